@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.{npz,json}.  Run HERE (the build container), where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Inputs : /root/reference/tests/images (PNG decoded with PIL; JPEG decoded with PIL/libjpeg -- NOT stb_image,
+         so the bbb* fixtures are live-parity inputs, not the reference's hard-coded bbb goldens).
+Outputs: decoded pixels + what the UNMODIFIED reference build (oracle/_ref) returns for them.
+The six einstein known answers are the reference's own constants (tests/rmgr-ssim-tests.cpp:354-359)."""
+import json
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from ssim_b200.synth import checksum, synth_pair  # noqa: E402
+
+IMAGES = "/root/reference/tests/images"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# reference tests/rmgr-ssim-tests.cpp:341-359 (files and their 18-digit known answers, double mean)
+EINSTEIN = [
+    ("einstein", "1.000000000000000000000000000000000"),
+    ("meanshift", "0.987345868581455342542598819456431"),
+    ("contrast", "0.901217091012390185892926336265424"),
+    ("impulse", "0.839533769204009687363862456348761"),
+    ("blur", "0.702192033056262932311859850040160"),
+    ("jpg", "0.669938383706498006524758818118705"),
+]
+
+EDGE_DIMS = [(1, 1), (2, 3), (7, 3), (5, 5), (11, 11), (16, 16), (255, 63), (256, 64), (257, 65), (300, 1),
+             (1, 300), (513, 129), (64, 75), (65, 11), (130, 200)]
+
+
+def f32(x):
+    return float(np.float32(x))
+
+
+def main():
+    oracle.build()
+    assert oracle.have_ref(), "needs /root/reference to build oracle/_ref"
+
+    # ---- einstein: 256x256 8-bit grayscale (BASELINE.json configs[0])
+    planes = {}
+    for name, _ in EINSTEIN:
+        img = Image.open(os.path.join(IMAGES, name + ".png"))
+        assert img.mode == "L" and img.size == (256, 256), (name, img.mode, img.size)
+        planes[name] = np.asarray(img, dtype=np.uint8).copy()
+    np.savez_compressed(os.path.join(OUT, "einstein.npz"), **planes)
+    ein = {}
+    ref = planes["einstein"]
+    for name, golden in EINSTEIN:
+        a = planes[name]
+        r64a, m64a = oracle.ref_ssim("f64", a, ref, want_map=True)
+        r64g, _ = oracle.ref_ssim("f64", a, ref, impl=oracle.IMPL_GENERIC)
+        r32, _ = oracle.ref_ssim("f32", a, ref, openmp=True)
+        ein[name] = {"golden_double_mean": golden, "ref_f64_auto": f32(r64a), "ref_f64_generic": f32(r64g),
+                     "ref_f32_auto_openmp": f32(r32),
+                     "ref_f64_auto_map_min": f32(m64a.min()), "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum())}
+    # one full map as a fixture (blur: lowest-scoring smooth case)
+    _, m = oracle.ref_ssim("f64", planes["blur"], ref, want_map=True)
+    np.savez_compressed(os.path.join(OUT, "einstein_blur_map_f64auto.npz"), map=m)
+
+    # ---- bbb 360p: RGB interleaved (step=3), crops 255x63 / 257x65 with the full-frame stride kept
+    png = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_360_07806.png")).convert("RGB"), dtype=np.uint8)
+    jpg = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_360_07806_50.jpg")).convert("RGB"), dtype=np.uint8)
+    assert png.shape == (360, 640, 3) and jpg.shape == png.shape
+    rows = 80  # keep the first 80 rows only (enough for the 65-row crop); stride stays 640*3
+    png, jpg = png[:rows].copy(), jpg[:rows].copy()
+    np.savez_compressed(os.path.join(OUT, "bbb360_top80.npz"), png=png, jpg50=jpg)
+    bbb = {}
+    for (w, h) in [(255, 63), (257, 65), (640, 80)]:
+        for ch in range(3):
+            kw = dict(step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, width=w, height=h, a_off=ch, b_off=ch)
+            r64a, m64a = oracle.ref_ssim("f64", jpg, png, want_map=True, **kw)
+            r64g, _ = oracle.ref_ssim("f64", jpg, png, impl=oracle.IMPL_GENERIC, **kw)
+            r32, _ = oracle.ref_ssim("f32", jpg, png, **kw)
+            bbb["%dx%d_ch%d" % (w, h, ch)] = {"ref_f64_auto": f32(r64a), "ref_f64_generic": f32(r64g), "ref_f32_auto": f32(r32),
+                                             "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum())}
+
+    # ---- synthetic recipe, seed 0x5517
+    syn = {}
+    for (w, h, f) in [(1920, 1080, 0), (1920, 1080, 1), (1920, 1080, 4095), (3840, 2160, 0)]:
+        a, b = synth_pair(w, h, f)
+        r64a, _ = oracle.ref_ssim("f64", a, b, openmp=True)
+        r64g, _ = oracle.ref_ssim("f64", a, b, impl=oracle.IMPL_GENERIC, openmp=True)
+        r32, _ = oracle.ref_ssim("f32", a, b, openmp=True)
+        syn["%dx%d_f%d" % (w, h, f)] = {"checksum": "%016x" % checksum(a, b), "ref_f64_auto": f32(r64a),
+                                        "ref_f64_generic": f32(r64g), "ref_f32_auto_openmp": f32(r32)}
+    a, b = synth_pair(16384, 16384, 0)
+    r64a, _ = oracle.ref_ssim("f64", a, b, openmp=True)
+    r32, _ = oracle.ref_ssim("f32", a, b, openmp=True)
+    syn["16384x16384_f0"] = {"ref_f64_auto": f32(r64a), "ref_f32_auto_openmp": f32(r32)}
+    for (w, h) in EDGE_DIMS:
+        a, b = synth_pair(w, h, 3)
+        r64a, m64a = oracle.ref_ssim("f64", a, b, want_map=True)
+        r64g, _ = oracle.ref_ssim("f64", a, b, impl=oracle.IMPL_GENERIC)
+        r32, _ = oracle.ref_ssim("f32", a, b)
+        syn["%dx%d_f3" % (w, h)] = {"ref_f64_auto": f32(r64a), "ref_f64_generic": f32(r64g), "ref_f32_auto": f32(r32),
+                                    "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum())}
+
+    with open(os.path.join(OUT, "golden.json"), "w") as fh:
+        json.dump({"einstein": ein, "bbb360_jpg50": bbb, "synthetic": syn,
+                   "note": "ref_* values are float32 results of the unmodified reference build (oracle/_ref), repr as double"},
+                  fh, indent=1, sort_keys=True)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+"""Pins the CPU oracle (oracle/ssim_oracle.c) -- CPU only, no GPU needed.
+
+ 1. against the reference's own decoder-independent known answers (tests/rmgr-ssim-tests.cpp:354-359),
+ 2. against golden vectors produced by the unmodified reference build and committed in tests/golden/,
+ 3. live against oracle/_ref (the reference compiled in place) when those libraries are present."""
+import numpy as np
+import pytest
+
+import oracle
+from ssim_b200.synth import checksum, synth_pair
+
+EINSTEIN = ["einstein", "meanshift", "contrast", "impulse", "blur", "jpg"]
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference once)")
+
+
+def test_taps_are_normalised_and_symmetric():
+    k = oracle.oracle_taps(oracle.TAPS_RUNTIME)
+    assert abs(k.sum() - 1.0) < 1e-15
+    assert np.array_equal(k, k.T) and np.array_equal(k, k[::-1, ::-1])
+    # separable up to double rounding: k == outer(g, g)
+    g = k.sum(axis=0)
+    assert np.abs(np.outer(g, g) - k).max() < 1e-16
+    t = oracle.oracle_taps(oracle.TAPS_TABLE)
+    # the float-pipeline table is biased: sum = 1 + 1.02e-8
+    assert 0.9e-8 < t.sum() - 1.0 < 1.2e-8
+    assert np.array_equal(t, t.T)
+
+
+@pytest.mark.parametrize("name", EINSTEIN)
+def test_einstein_known_answers(name, einstein, golden):
+    """reference tests/rmgr-ssim-tests.cpp:354-359, REF_TOLERANCE 1e-13 (:64-73)"""
+    a, ref = einstein[name], einstein["einstein"]
+    _, total, _ = oracle.oracle_ssim(a, ref, taps=oracle.TAPS_RUNTIME)
+    known = float(golden["einstein"][name]["golden_double_mean"])
+    assert abs(total / (256 * 256) - known) < 1e-13
+
+
+@pytest.mark.parametrize("name", EINSTEIN)
+def test_einstein_matches_reference_build_vectors(name, einstein, golden):
+    a, ref = einstein[name], einstein["einstein"]
+    g = golden["einstein"][name]
+    s1, _, m1 = oracle.oracle_ssim(a, ref, want_map=True, taps=oracle.TAPS_TABLE)
+    s2, _, _ = oracle.oracle_ssim(a, ref, taps=oracle.TAPS_RUNTIME)
+    assert abs(float(s1) - g["ref_f64_auto"]) <= 6e-8        # one float ulp
+    assert abs(float(s2) - g["ref_f64_generic"]) <= 6e-8
+    assert abs(m1.astype(np.float64).sum() - g["ref_f64_auto_map_sum64"]) < 1e-6
+
+
+def test_einstein_map_fixture(einstein):
+    import os
+    from conftest import GOLDEN_DIR
+    want = np.load(os.path.join(GOLDEN_DIR, "einstein_blur_map_f64auto.npz"))["map"]
+    _, _, got = oracle.oracle_ssim(einstein["blur"], einstein["einstein"], want_map=True, taps=oracle.TAPS_TABLE)
+    assert np.abs(got - want).max() <= 1.2e-7
+
+
+@pytest.mark.parametrize("dims", [(255, 63), (257, 65), (640, 80)])
+@pytest.mark.parametrize("ch", [0, 1, 2])
+def test_bbb_interleaved_crops(dims, ch, bbb360, golden):
+    """step = 3, stride != width*step, one-tile-minus/plus-one shapes (reference tests :428-465)"""
+    w, h = dims
+    g = golden["bbb360_jpg50"]["%dx%d_ch%d" % (w, h, ch)]
+    s, _, m = oracle.oracle_ssim(bbb360["jpg50"], bbb360["png"], want_map=True, taps=oracle.TAPS_TABLE,
+                                 step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, width=w, height=h, a_off=ch, b_off=ch)
+    assert abs(float(s) - g["ref_f64_auto"]) <= 6e-8
+    assert abs(m.astype(np.float64).sum() - g["ref_f64_auto_map_sum64"]) < 1e-6
+
+
+def test_synthetic_recipe_checksums(golden):
+    for key in ["1920x1080_f0", "1920x1080_f1"]:
+        w, h = map(int, key.split("_")[0].split("x"))
+        f = int(key.split("_f")[1])
+        a, b = synth_pair(w, h, f)
+        assert "%016x" % checksum(a, b) == golden["synthetic"][key]["checksum"]
+    # strips of a frame are slices of the frame
+    a, b = synth_pair(300, 40, 2)
+    a2, b2 = synth_pair(300, 15, 2, y0=25)
+    assert np.array_equal(a[25:], a2) and np.array_equal(b[25:], b2)
+
+
+@pytest.mark.parametrize("key", ["1x1_f3", "2x3_f3", "7x3_f3", "5x5_f3", "11x11_f3", "16x16_f3", "255x63_f3", "256x64_f3",
+                                 "257x65_f3", "300x1_f3", "1x300_f3", "513x129_f3", "64x75_f3", "65x11_f3", "130x200_f3"])
+def test_edge_dims_vectors(key, golden):
+    w, h = map(int, key.split("_")[0].split("x"))
+    a, b = synth_pair(w, h, 3)
+    g = golden["synthetic"][key]
+    s1, _, m = oracle.oracle_ssim(a, b, want_map=True, taps=oracle.TAPS_TABLE)
+    s2, _, _ = oracle.oracle_ssim(a, b, taps=oracle.TAPS_RUNTIME)
+    assert abs(float(s1) - g["ref_f64_auto"]) <= 6e-8
+    assert abs(float(s2) - g["ref_f64_generic"]) <= 6e-8
+    assert abs(m.astype(np.float64).sum() - g["ref_f64_auto_map_sum64"]) < 1e-7 * max(1, w * h)
+
+
+def test_synthetic_1080p_vector(golden):
+    a, b = synth_pair(1920, 1080, 0)
+    s1, _, _ = oracle.oracle_ssim(a, b, taps=oracle.TAPS_TABLE)
+    assert abs(float(s1) - golden["synthetic"]["1920x1080_f0"]["ref_f64_auto"]) <= 6e-8
+
+
+def test_argument_errors():
+    import ctypes as C
+    lib = oracle.oracle_lib()
+    a = np.zeros((4, 4), np.uint8)
+    s = C.c_float()
+    assert lib.ssim_oracle_compute(4, 4, a.ctypes.data, 1, 4, a.ctypes.data, 1, 4, None, 0, 0, 0, None, None) == 22
+    assert lib.ssim_oracle_compute(4, 4, None, 1, 4, a.ctypes.data, 1, 4, None, 0, 0, 0, C.byref(s), None) == 22
+    assert lib.ssim_oracle_compute(0, 4, a.ctypes.data, 1, 4, a.ctypes.data, 1, 4, None, 0, 0, 0, C.byref(s), None) == 22
+
+
+def test_negative_strides_and_identity():
+    """flipping both images leaves the global SSIM unchanged; identical images give exactly 1"""
+    a, b = synth_pair(97, 41, 5)
+    s, _, m = oracle.oracle_ssim(a, b, want_map=True)
+    n = a.size
+    sf, _, mf = oracle.oracle_ssim(a, b, want_map=True, stride_a=-97, stride_b=-97, a_off=n - 97, b_off=n - 97, width=97, height=41)
+    assert abs(float(s) - float(sf)) < 1e-7 and np.abs(m[::-1] - mf).max() < 1e-6
+    s1, _, m1 = oracle.oracle_ssim(a, a, want_map=True)
+    assert s1 == np.float32(1.0) and (m1 == 1.0).all()
+
+
+# ------------------------------------------------------------------ live against the reference build
+@needs_ref
+@pytest.mark.parametrize("dims", [(1, 1), (3, 2), (33, 9), (256, 64), (300, 70), (517, 131)])
+def test_live_against_reference_random(dims):
+    w, h = dims
+    rng = np.random.default_rng(w * 1000 + h)
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    b = np.clip(a.astype(np.int32) + rng.integers(-20, 21, (h, w)), 0, 255).astype(np.uint8)
+    s1, _, m1 = oracle.oracle_ssim(a, b, want_map=True, taps=oracle.TAPS_TABLE)
+    r1, rm1 = oracle.ref_ssim("f64", a, b, want_map=True)
+    assert abs(float(s1) - float(r1)) <= 6e-8 and np.abs(m1 - rm1).max() <= 1.2e-7
+    s2, _, m2 = oracle.oracle_ssim(a, b, want_map=True, taps=oracle.TAPS_RUNTIME)
+    r2, rm2 = oracle.ref_ssim("f64", a, b, want_map=True, impl=oracle.IMPL_GENERIC)
+    assert abs(float(s2) - float(r2)) <= 6e-8 and np.abs(m2 - rm2).max() <= 1.2e-7
+
+
+@needs_ref
+def test_reference_builds_are_what_they_claim():
+    assert oracle.ref_lib("f32").ref_uses_double() == 0
+    assert oracle.ref_lib("f64").ref_uses_double() == 1
+    # AUTO on x86 picks FMA when available: mask has generic|auto at least
+    assert oracle.ref_lib("f32").ref_select_impl(0) & 0x3 == 0x3
