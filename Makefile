@@ -1,0 +1,36 @@
+# Builds the product libraries in-tree:
+#   ssim_b200/lib/libssim_cuda.so   C-ABI shim + sm_100a kernels   (include/ssim_cuda.h)
+#   ssim_b200/lib/librmgr-ssim.so   the reference's C/C++ API      (include/rmgr/ssim.h, ssim-openmp.h)
+# `make oracle` builds the CPU checkers (test infrastructure) under oracle/.
+NVCC    ?= /usr/local/cuda/bin/nvcc
+HOSTCXX ?= /usr/bin/g++
+ARCH    := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin $(HOSTCXX) -Iinclude -Issim_b200/csrc
+CSRC    := ssim_b200/csrc
+LIB     := ssim_b200/lib
+OBJ     := build/obj
+
+all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so
+
+$(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/ssim_kernels.h $(CSRC)/synth.h include/ssim_cuda.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJ)/%.o: $(CSRC)/%.cpp include/ssim_cuda.h include/rmgr/ssim.h
+	@mkdir -p $(OBJ)
+	$(HOSTCXX) -O2 -std=c++17 -fPIC -DNDEBUG -Iinclude -I/usr/local/cuda/include -c $< -o $@
+
+$(LIB)/libssim_cuda.so: $(OBJ)/ssim_kernels.o $(OBJ)/ssim_cuda.o
+	@mkdir -p $(LIB)
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $^ -cudart static -ldl -lpthread
+
+$(LIB)/librmgr-ssim.so: $(OBJ)/rmgr_api.o $(LIB)/libssim_cuda.so
+	$(HOSTCXX) -shared -o $@ $(OBJ)/rmgr_api.o -L$(LIB) -lssim_cuda -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all oracle clean

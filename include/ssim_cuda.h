@@ -1,0 +1,106 @@
+/*
+ * ssim_cuda.h -- C ABI of libssim_cuda.so, the CUDA (sm_100a) engine under rmgr::ssim.
+ *
+ * Plain C types only (pointers, sizes, errno-style int returns); no C++/CUDA/torch types cross this
+ * boundary, so it can be bound from C, C++, ctypes, cgo, JNI ...  librmgr-ssim.so (the reference's
+ * API, include/rmgr/ssim.h) is a thin C++ layer over these calls.
+ *
+ * What each entry point replaces in the reference:
+ *   ssim_cuda_compute()          the body of rmgr::ssim::compute_ssim() after parameter validation:
+ *                                Gaussian set-up, the 256x64 tile loop / thread-pool dispatch and the
+ *                                final mean (reference src/ssim.cpp:990-1103), i.e. process_tile()
+ *                                (:747-783) = retrieve_tile (:515-583) + multiply x3 (:249-265) +
+ *                                gaussian_blur x5 (:321-489, ISA variants src/ssim_{sse,avx,fma,neon}.cpp)
+ *                                + sum_tile (:590-704), and run_in_openmp (src/ssim-openmp.c:26-37)
+ *   ssim_cuda_compute_device()   the same, for callers that already hold the planes in device memory
+ *                                (frames / strips; BASELINE.json configs 2-5).  No reference equivalent:
+ *                                the reference has no device or batch notion; this is the entry the
+ *                                bench and multi-GPU drivers use.
+ *   ssim_cuda_compute_strips()   one large image split into row strips across several GPUs of one
+ *                                process, partial sums combined with an NCCL all-reduce; replaces the
+ *                                OpenMP tile distribution for gigapixel inputs (src/ssim-openmp.c:26-47)
+ *
+ * Return values: 0, EINVAL, ENOMEM, ENODEV (no usable device), EIO (CUDA/NCCL runtime failure; text in
+ * ssim_cuda_last_error_string()).  All functions are thread-safe; a call never retains caller pointers.
+ */
+#ifndef SSIM_CUDA_H
+#define SSIM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSIM_CUDA_ABI_VERSION 1
+
+int         ssim_cuda_abi_version(void);
+int         ssim_cuda_device_count(void);            /* 0 when there is no driver / device */
+int         ssim_cuda_init(int device);              /* optional: creates the per-device context eagerly */
+void        ssim_cuda_shutdown(void);                /* releases every context; safe to call twice */
+const char* ssim_cuda_last_error_string(void);       /* thread-local, never NULL */
+
+/* Pinned host memory for callers that want the fastest host path (optional; any host memory works). */
+void* ssim_cuda_host_alloc(size_t bytes);
+void  ssim_cuda_host_free(void* p);
+
+/*
+ * One image pair, any layout.  Pixel (x,y) of image A is a[x*stepA + y*strideA] (bytes, signed);
+ * map pixel (x,y) is map[x*mapStep + y*mapStride] (floats, signed).  `a`, `b`, `map` may each be host
+ * or device pointers.  `ssim` (host) and `map` may be NULL, but not both.  Blocking.
+ * Semantics: 11x11 Gaussian window sigma 1.5, C1=(0.01*255)^2, C2=(0.03*255)^2, clamp-to-edge borders,
+ * float per-pixel values, double global sum, *ssim = float(sum / double(uint32(width*height))).
+ */
+int ssim_cuda_compute(int device, uint32_t width, uint32_t height,
+                      const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                      const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                      float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                      float* ssim);
+
+/*
+ * Device-resident planes, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ * stream).  `frames` independent pairs are processed by ONE kernel launch (+ one small reduction launch).
+ *
+ *   dA/dB      8-bit planes, 1 byte per pixel; pixel (x,y) of frame f at d[f*frameStride + y*pitch + x].
+ *              Base address, pitch and frameStride must be multiples of 16 bytes (TMA requirement).
+ *   srcRows    rows present in each plane; rows outside [0,srcRows) replicate the nearest one.
+ *   outY0,outRows  the rows for which SSIM is produced: a full image uses (0, srcRows); a strip that
+ *              carries 5 halo rows on an interior edge uses outY0 = 5 there.  Columns always clamp at
+ *              [0,width).
+ *   dMap       NULL, or floats: value of (x, outY0+r) of frame f at dMap[f*mapFrameStride + r*mapPitch + x]
+ *   dSums      NULL or [frames] doubles: sum of the SSIM values of the outRows x width outputs
+ *   dSsim      NULL or [frames] floats : float(sum / double(uint32(width*outRows)))
+ */
+int ssim_cuda_compute_device(int device, void* stream,
+                             uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,
+                             const uint8_t* dA, size_t pitchA, size_t frameStrideA,
+                             const uint8_t* dB, size_t pitchB, size_t frameStrideB,
+                             float* dMap, size_t mapPitch, size_t mapFrameStride,
+                             double* dSums, float* dSsim);
+
+/* Number of kernels the previous ssim_cuda_compute_device() call on this thread launched (for bench.py) */
+int ssim_cuda_last_launch_count(void);
+
+/*
+ * One host image pair split into horizontal strips (with 5 halo rows on interior edges) across
+ * `nDevices` GPUs of this process; the per-GPU double sums are combined with ncclAllReduce.
+ * Same argument meaning as ssim_cuda_compute(); pointers must be host pointers.
+ */
+int ssim_cuda_compute_strips(int nDevices, const int* devices, uint32_t width, uint32_t height,
+                             const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                             const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                             float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                             float* ssim);
+
+/* Fills device planes with rows y0..y0+rows-1 of synthetic frame `frame` (ssim_b200/csrc/synth.h). */
+int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, uint8_t* dB, size_t pitchB,
+                         uint32_t width, uint32_t rows, uint32_t y0, uint32_t frame, uint64_t seed);
+
+/* Tuning knob (0 = automatic): rows per warp work item of the fused kernel.  For experiments/bench only. */
+void ssim_cuda_set_segment_rows(int rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSIM_CUDA_H */

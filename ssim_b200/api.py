@@ -1,0 +1,129 @@
+"""ctypes binding of the product libraries (no torch needed):
+
+  librmgr-ssim.so   the reference's C API  -- rmgr_ssim_compute_ssim() & friends (include/rmgr/ssim.h)
+  libssim_cuda.so   the C-ABI CUDA engine  -- ssim_cuda_*()                      (include/ssim_cuda.h)
+
+There is no CPU fallback: importing works anywhere, but every compute call needs the built libraries and a
+B200; a missing library raises immediately (RuntimeError) instead of degrading."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import Params, ThreadPool, Version, bind_reference_api, make_params
+
+LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+_libs = {}
+
+
+def _load(name):
+    if name not in _libs:
+        path = os.path.join(LIB_DIR, name)
+        if not os.path.exists(path):
+            raise RuntimeError("%s is not built (run `make` or __graft_entry__.build()); ssim_b200 has no CPU fallback" % path)
+        _libs[name] = C.CDLL(path, mode=os.RTLD_LOCAL)
+    return _libs[name]
+
+
+def cuda_lib():
+    """libssim_cuda.so with argtypes declared for every symbol of include/ssim_cuda.h."""
+    lib = _load("libssim_cuda.so")
+    if getattr(lib, "_bound", False):
+        return lib
+    u8p, f32p, f64p, vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    lib.ssim_cuda_abi_version.restype = C.c_int
+    lib.ssim_cuda_device_count.restype = C.c_int
+    lib.ssim_cuda_init.argtypes = [C.c_int]
+    lib.ssim_cuda_init.restype = C.c_int
+    lib.ssim_cuda_shutdown.restype = None
+    lib.ssim_cuda_last_error_string.restype = C.c_char_p
+    lib.ssim_cuda_host_alloc.argtypes = [C.c_size_t]
+    lib.ssim_cuda_host_alloc.restype = C.c_void_p
+    lib.ssim_cuda_host_free.argtypes = [C.c_void_p]
+    lib.ssim_cuda_host_free.restype = None
+    lib.ssim_cuda_compute.argtypes = [C.c_int, C.c_uint32, C.c_uint32, u8p, C.c_ssize_t, C.c_ssize_t, u8p, C.c_ssize_t, C.c_ssize_t,
+                                      f32p, C.c_ssize_t, C.c_ssize_t, C.POINTER(C.c_float)]
+    lib.ssim_cuda_compute.restype = C.c_int
+    lib.ssim_cuda_compute_device.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                             u8p, C.c_size_t, C.c_size_t, u8p, C.c_size_t, C.c_size_t,
+                                             f32p, C.c_size_t, C.c_size_t, f64p, f32p]
+    lib.ssim_cuda_compute_device.restype = C.c_int
+    lib.ssim_cuda_last_launch_count.restype = C.c_int
+    lib.ssim_cuda_compute_strips.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, u8p, C.c_ssize_t, C.c_ssize_t,
+                                             u8p, C.c_ssize_t, C.c_ssize_t, f32p, C.c_ssize_t, C.c_ssize_t, C.POINTER(C.c_float)]
+    lib.ssim_cuda_compute_strips.restype = C.c_int
+    lib.ssim_cuda_synth_fill.argtypes = [C.c_int, vp, u8p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_uint32, C.c_uint64]
+    lib.ssim_cuda_synth_fill.restype = C.c_int
+    lib.ssim_cuda_set_segment_rows.argtypes = [C.c_int]
+    lib.ssim_cuda_set_segment_rows.restype = None
+    lib._bound = True
+    return lib
+
+
+def rmgr_lib():
+    """librmgr-ssim.so with the reference API's argtypes."""
+    cuda_lib()  # dependency, loaded first so the $ORIGIN rpath is not even needed
+    lib = _load("librmgr-ssim.so")
+    if not getattr(lib, "_bound", False):
+        bind_reference_api(lib)
+        lib._bound = True
+    return lib
+
+
+class SsimError(OSError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise SsimError(rc, "%s (%s)" % (os.strerror(rc), cuda_lib().ssim_cuda_last_error_string().decode()))
+
+
+def get_version():
+    v = Version()
+    _check(rmgr_lib().rmgr_ssim_get_version(C.byref(v)))
+    return v.major, v.minor, v.patch, v.string.decode()
+
+
+def compute_ssim(a, b, want_map=False, want_ssim=True, width=None, height=None, step_a=1, step_b=1, stride_a=None,
+                 stride_b=None, a_off=0, b_off=0, ssim_map=None, map_step=1, map_stride=None, map_off=0, openmp=False,
+                 thread_pool=None):
+    """rmgr_ssim_compute_ssim() on numpy uint8 buffers (host memory).  Returns (ssim or None, map or None).
+
+    Mirrors the reference call: Params{width,height,imgA,imgB,ssimMap,ssimStep,ssimStride} (include/rmgr/ssim.h)."""
+    if width is None:
+        height, width = a.shape[:2]
+    if want_map and ssim_map is None:
+        ssim_map = np.empty((height, width), dtype=np.float32)
+    p = make_params(a, b, width, height, step_a, stride_a, step_b, stride_b, ssim_map, map_step, map_stride, a_off, b_off, map_off)
+    out = C.c_float()
+    lib = rmgr_lib()
+    if openmp:
+        rc = lib.rmgr_ssim_compute_ssim_openmp(C.byref(out) if want_ssim else None, C.byref(p))
+    else:
+        rc = lib.rmgr_ssim_compute_ssim(C.byref(out) if want_ssim else None, C.byref(p), thread_pool)
+    _check(rc)
+    return (np.float32(out.value) if want_ssim else None), ssim_map
+
+
+def compute_device(device, stream, width, src_rows, out_y0, out_rows, frames, d_a, pitch_a, fstride_a, d_b, pitch_b, fstride_b,
+                   d_map=None, map_pitch=0, map_fstride=0, d_sums=None, d_ssim=None):
+    """ssim_cuda_compute_device(): raw device addresses (ints), asynchronous on `stream` (int handle or None)."""
+    _check(cuda_lib().ssim_cuda_compute_device(device, stream, width, src_rows, out_y0, out_rows, frames, d_a, pitch_a, fstride_a,
+                                              d_b, pitch_b, fstride_b, d_map, map_pitch, map_fstride, d_sums, d_ssim))
+
+
+def compute_strips(devices, a, b, want_map=False):
+    """ssim_cuda_compute_strips() on dense numpy uint8 images; returns (ssim, map or None)."""
+    h, w = a.shape
+    m = np.empty((h, w), dtype=np.float32) if want_map else None
+    out = C.c_float()
+    devs = (C.c_int * len(devices))(*devices)
+    _check(cuda_lib().ssim_cuda_compute_strips(len(devices), devs, w, h, a.ctypes.data, 1, w, b.ctypes.data, 1, w,
+                                              m.ctypes.data if want_map else None, 1, w, C.byref(out)))
+    return np.float32(out.value), m
+
+
+def synth_fill(device, stream, d_a, pitch_a, d_b, pitch_b, width, rows, y0=0, frame=0, seed=0x5517):
+    _check(cuda_lib().ssim_cuda_synth_fill(device, stream, d_a, pitch_a, d_b, pitch_b, width, rows, y0, frame, seed))

@@ -1,0 +1,677 @@
+// ssim_cuda.cu -- runtime behind the C ABI of include/ssim_cuda.h.
+//
+// Host-side responsibilities (everything the reference's compute_ssim() does around its tile loop,
+// src/ssim.cpp:956-1103, re-thought for a GPU):
+//   * per-device context: streams, grow-only device scratch (canonical A/B planes, dense map, partial sums),
+//     pinned staging, cached kernel geometry
+//   * bringing ANY (step, stride, host|device) image into the canonical layout the fused kernel wants
+//     (1 byte/pixel, 16-byte aligned base and pitch => TMA-legal): cudaMemcpy2DAsync for the common host case,
+//     footprint copy + pack kernel for interleaved / negative-stride / column-major layouts
+//   * work decomposition of (frames x rows x 64-column bands) into warp items sized to the 148-SM machine
+//   * TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed)
+//   * getting the map back out in the caller's layout, and the final float(sum / double(W*H))
+// There is deliberately no CPU fallback: without a device every compute entry point returns ENODEV.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "ssim_cuda.h"
+#include "ssim_kernels.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ errors
+thread_local char g_err[512] = "";
+thread_local int  g_lastLaunches = 0;
+int g_segRowsOverride = 0;
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("SSIM_CUDA_VERBOSE")) fprintf(stderr, "ssim_cuda: %s\n", g_err);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    if (e == cudaErrorMemoryAllocation) return fail(ENOMEM, "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice)
+        return fail(ENODEV, "%s: %s", what, cudaGetErrorString(e));
+    return fail(EIO, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU_TRY(expr)                                                   \
+    do {                                                               \
+        cudaError_t e__ = (expr);                                      \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr);          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ Gaussian taps
+// The window every shipped build of the reference actually applies is its FLOAT 11x11 kernel: the generic blur
+// computes it at run time (src/ssim.cpp:272-318, Float = float) and all SIMD blurs carry the same values as a
+// literal table, even in the double build (src/ssim_fma.cpp:164-175).  Each of those 121 taps is rounded
+// separately, so the window sums to 1 + 1.02e-8 instead of 1; that bias moves every variance by -1e-8 mu^2
+// and the global SSIM of the double build by up to 1.7e-6 (tests/golden: ref_f64_auto vs ref_f64_generic).
+// To reproduce the reference rather than the ideal Gaussian we
+//   1. rebuild that float window exactly as the reference does,
+//   2. take its best separable (rank-1, symmetric) approximation g g^T by power iteration in double,
+//   3. round g to float and nudge the three outermost taps by a few ulps so that (sum g)^2 equals the window's sum.
+// In double arithmetic the resulting separable filter is within 3e-8 of the reference's double build.
+void gaussian_taps(float g[6])
+{
+    const int R = 5, N = 11;
+    const float sigma = 1.5f, sigma2 = sigma * sigma;
+    float kf[N * N];
+    double sum = 0.0;
+    for (int y = 0; y < N; ++y)
+        for (int x = 0; x < N; ++x) {
+            const float num = expf(-(float)((x - R) * (x - R) + (y - R) * (y - R)) / (2 * sigma2));
+            kf[y * N + x] = num / ((float)(2 * M_PI) * sigma2);
+            sum += (double)kf[y * N + x];
+        }
+    double T[N * N], total = 0.0;
+    for (int i = 0; i < N * N; ++i) { T[i] = (double)(kf[i] / (float)sum); total += T[i]; }
+
+    double v[N], t[N];
+    for (int i = 0; i < N; ++i) v[i] = 1.0 / std::sqrt((double)N);
+    double lambda = 0.0;
+    for (int it = 0; it < 200; ++it) {
+        double norm = 0.0;
+        for (int i = 0; i < N; ++i) { t[i] = 0.0; for (int j = 0; j < N; ++j) t[i] += T[i * N + j] * v[j]; norm += t[i] * t[i]; }
+        norm = std::sqrt(norm);
+        lambda = 0.0;
+        for (int i = 0; i < N; ++i) { lambda += v[i] * t[i]; v[i] = t[i] / norm; }
+    }
+    for (int d = 0; d <= R; ++d) g[d] = (float)(std::sqrt(lambda) * 0.5 * (v[R - d] + v[R + d]));
+
+    const double target = std::sqrt(total);
+    for (int d = 3; d <= R; ++d) {
+        double s = (double)g[0];
+        for (int k = 1; k <= R; ++k) s += 2.0 * (double)g[k];
+        const double ulp = (double)(std::nextafterf(g[d], 1.0f) - g[d]);
+        g[d] = (float)((double)g[d] + std::nearbyint((target - s) / (2.0 * ulp)) * ulp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+int make_plane_map(CUtensorMap* tm, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
+                   size_t frameStride, uint32_t boxRows)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(EIO, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3]    = {width, rows, frames};
+    const cuuint64_t strides[2] = {pitch, frames > 1 ? frameStride : (cuuint64_t)pitch * rows};
+    const cuuint32_t box[3]     = {(cuuint32_t)ssimk::kBoxW, boxRows, 1};
+    const cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EIO, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u pitch %zu", (int)r, width, rows, frames, pitch);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device context
+struct Buffer {
+    void*  ptr = nullptr;
+    size_t cap = 0;
+    bool   pinnedHost = false;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        release();
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = pinnedHost ? cudaMallocHost(&ptr, want) : cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) { ptr = nullptr; cap = 0; cudaGetLastError(); return fail(ENOMEM, "allocating %zu bytes of %s memory failed", want, pinnedHost ? "pinned host" : "device"); }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (ptr) { if (pinnedHost) cudaFreeHost(ptr); else cudaFree(ptr); }
+        ptr = nullptr; cap = 0;
+    }
+};
+
+struct Context {
+    int device = -1;
+    int numSMs = 0;
+    int ctasPerSm = 3;
+    cudaStream_t stream = nullptr;            // stream of the blocking host-pointer path
+    std::mutex hostPathMutex;                 // the host path shares the scratch below
+    Buffer planeA, planeB, rawA, rawB, map, stage;
+    Buffer scalars;                           // double sum + float ssim of the host path
+    std::mutex wsMutex;
+    std::map<cudaStream_t, Buffer> partials;  // per-stream partial-sum workspace of compute_device
+    float taps[6];
+};
+
+std::mutex g_ctxMutex;
+std::map<int, Context*> g_ctx;
+
+int get_context(int device, Context** out)
+{
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) { *out = it->second; return 0; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return fail(ENODEV, "no usable CUDA device (%s)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)); }
+    if (device < 0 || device >= count) return fail(EINVAL, "device %d out of range [0,%d)", device, count);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    Context* c = new Context();
+    c->device = device;
+    c->numSMs = prop.multiProcessorCount;
+    c->stage.pinnedHost = true;
+    gaussian_taps(c->taps);
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int regsMap = 0, regsNoMap = 0, ctas = 0;
+    CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &ctas));
+    c->ctasPerSm = std::max(1, ctas);
+    g_ctx[device] = c;
+    *out = c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ work decomposition
+// A work item is (frame, row segment, 64-column band) and is executed by one warp.  Each item pays a fixed
+// 10-row halo (horizontal pass recomputed, vertical pipeline fill), so segments should be tall; but a single
+// 4K image only has 60 bands, so segments must also be numerous enough to occupy ctasPerSm*4 warps on every SM.
+void choose_segments(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, int* segRows, int* segs)
+{
+    const long long bands = (width + ssimk::kBandW - 1) / ssimk::kBandW;
+    const long long slots = (long long)c->numSMs * c->ctasPerSm * ssimk::kWarpsPerCta;   // resident warps
+    const long long units = bands * frames;
+    long long s;
+    if (g_segRowsOverride > 0) {
+        s = (outRows + g_segRowsOverride - 1) / g_segRowsOverride;
+    } else if (units * ((outRows + 63) / 64) <= slots) {
+        s = (outRows + 63) / 64;                       // tiny problem: segments of >= 64 rows, less than one wave
+    } else if (units >= slots) {
+        // several waves anyway: aim for >= 8 waves of items, keep segments >= 128 rows
+        s = std::max<long long>(1, std::min<long long>((8 * slots + units - 1) / units, outRows / 128));
+    } else {
+        s = std::max<long long>(1, slots / units);     // exactly one wave, as full as possible
+    }
+    s = std::max<long long>(1, std::min<long long>(s, outRows));
+    int rows = (int)((outRows + s - 1) / s);
+    *segRows = rows;
+    *segs = (int)((outRows + rows - 1) / rows);
+}
+
+int get_partials(Context* c, cudaStream_t stream, size_t bytes, double** out)
+{
+    std::lock_guard<std::mutex> lock(c->wsMutex);
+    Buffer& b = c->partials[stream];
+    if (bytes > b.cap) {
+        // the old buffer may still be in use by work queued on this stream
+        if (b.ptr) CU_TRY(cudaStreamSynchronize(stream));
+        int rc = b.ensure(std::max<size_t>(bytes, 1 << 20));
+        if (rc) return rc;
+    }
+    *out = (double*)b.ptr;
+    return 0;
+}
+
+int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
+                        uint32_t frames, const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB,
+                        size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim)
+{
+    g_lastLaunches = 0;
+    if (width == 0 || srcRows == 0 || outRows == 0 || frames == 0) return fail(EINVAL, "width, rows and frames must be non-zero");
+    if (dA == nullptr || dB == nullptr) return fail(EINVAL, "dA or dB is NULL");
+    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr) return fail(EINVAL, "no output requested");
+    if ((uint64_t)outY0 + outRows > srcRows) return fail(EINVAL, "output rows [%u,%u) exceed the %u source rows", outY0, outY0 + outRows, srcRows);
+    if (width > 0x7fffff00u || srcRows > 0x7fffff00u) return fail(EINVAL, "dimensions too large");
+    if (((uintptr_t)dA | (uintptr_t)dB | pitchA | pitchB) & 15) return fail(EINVAL, "plane base addresses and pitches must be multiples of 16 bytes");
+    if (frames > 1 && ((frameStrideA | frameStrideB) & 15)) return fail(EINVAL, "frame strides must be multiples of 16 bytes");
+    if (pitchA < width || pitchB < width) return fail(EINVAL, "pitch smaller than width");
+    if (dMap && mapPitch < width) return fail(EINVAL, "map pitch smaller than width");
+
+    int segRows, segs;
+    choose_segments(c, width, outRows, frames, &segRows, &segs);
+    const int bands = (int)((width + ssimk::kBandW - 1) / ssimk::kBandW);
+    const long long itemsPerFrame = (long long)bands * segs;
+    const long long items = itemsPerFrame * frames;
+    if (itemsPerFrame > 0x7fffffffLL) return fail(EINVAL, "image too large");
+
+    double* partials = nullptr;
+    int rc = get_partials(c, stream, (size_t)items * sizeof(double), &partials);
+    if (rc) return rc;
+
+    CUtensorMap tmA8, tmA1, tmB8, tmB1;
+    if ((rc = make_plane_map(&tmA8, dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kBlkRows))) return rc;
+    if ((rc = make_plane_map(&tmA1, dA, width, srcRows, frames, pitchA, frameStrideA, 1))) return rc;
+    if ((rc = make_plane_map(&tmB8, dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kBlkRows))) return rc;
+    if ((rc = make_plane_map(&tmB1, dB, width, srcRows, frames, pitchB, frameStrideB, 1))) return rc;
+
+    ssimk::FusedParams p;
+    memset(&p, 0, sizeof(p));
+    p.a = dA; p.b = dB;
+    p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
+    p.pitchB = (long long)pitchB; p.frameStrideB = (long long)frameStrideB;
+    p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride;
+    p.partials = partials;
+    p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
+    p.bands = bands; p.segs = segs; p.segRows = segRows; p.items = items;
+    for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];
+    p.c1 = (float)((0.01 * 255) * (0.01 * 255));      // src/ssim.cpp:956-960
+    p.c2 = (float)((0.03 * 255) * (0.03 * 255));
+    {
+        double s1 = (double)c->taps[0];
+        for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];
+        p.eps2 = (float)(2.0 * (s1 * s1 - 1.0));
+    }
+    CU_TRY(ssimk::launch_fused(stream, tmA8, tmA1, tmB8, tmB1, p));
+    g_lastLaunches = 1;
+
+    if (dSums || dSsim) {
+        ssimk::FinalizeParams f;
+        f.partials = partials; f.sums = dSums; f.ssim = dSsim;
+        f.itemsPerFrame = (int)itemsPerFrame;
+        f.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
+        CU_TRY(ssimk::launch_finalize(stream, f, (int)frames));
+        g_lastLaunches = 2;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ general path
+enum class Where { Host, Device };
+
+Where classify(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return Where::Host; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? Where::Device : Where::Host;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Brings one strided image into a canonical plane (dense rows, 16-byte aligned pitch) in device memory.
+// On return *plane/*pitch describe it; it is either the caller's own memory (already canonical) or ctx scratch.
+int canonical_plane(Context* c, cudaStream_t s, const uint8_t* img, ptrdiff_t step, ptrdiff_t stride, uint32_t W, uint32_t H,
+                    Buffer& planeBuf, Buffer& rawBuf, const uint8_t** plane, size_t* pitch)
+{
+    const Where where = classify(img);
+    const size_t canonPitch = align_up(W, 16);
+    if (where == Where::Device && step == 1 && stride >= (ptrdiff_t)W && (stride & 15) == 0 && ((uintptr_t)img & 15) == 0) {
+        *plane = img; *pitch = (size_t)stride;
+        return 0;
+    }
+    int rc = planeBuf.ensure(canonPitch * H);
+    if (rc) return rc;
+    uint8_t* dst = (uint8_t*)planeBuf.ptr;
+    *plane = dst; *pitch = canonPitch;
+    if (where == Where::Host && step == 1 && stride >= (ptrdiff_t)W) {
+        CU_TRY(cudaMemcpy2DAsync(dst, canonPitch, img, (size_t)stride, W, H, cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    if (where == Where::Device) {
+        CU_TRY(ssimk::launch_pack_u8(s, dst, (long long)canonPitch, img, step, stride, (int)W, (int)H));
+        return 0;
+    }
+    // host image with a general layout (interleaved channels, bottom-up, column-major ...): copy the byte range that
+    // contains every addressed pixel, then gather on the device.
+    const ptrdiff_t xExt = (ptrdiff_t)(W - 1) * step, yExt = (ptrdiff_t)(H - 1) * stride;
+    const ptrdiff_t lo = std::min<ptrdiff_t>(0, xExt) + std::min<ptrdiff_t>(0, yExt);
+    const ptrdiff_t hi = std::max<ptrdiff_t>(0, xExt) + std::max<ptrdiff_t>(0, yExt);
+    const size_t span = (size_t)(std::abs(xExt)) + 1;             // bytes touched in one row
+    const size_t absStride = (size_t)std::abs(stride);
+    if (absStride >= span && H > 1) {
+        // row-major-like: 2-D copy of H rows of `span` bytes
+        const size_t rawPitch = align_up(span, 16);
+        if ((rc = rawBuf.ensure(rawPitch * H))) return rc;
+        const uint8_t* firstRow = img + std::min<ptrdiff_t>(0, xExt) + std::min<ptrdiff_t>(0, yExt);   // lowest row start
+        CU_TRY(cudaMemcpy2DAsync(rawBuf.ptr, rawPitch, firstRow, absStride, span, H, cudaMemcpyHostToDevice, s));
+        // device address of pixel (0,0): row index in the copy is y (stride>0) or H-1-y (stride<0)
+        const uint8_t* d0 = (const uint8_t*)rawBuf.ptr + (stride < 0 ? (size_t)(H - 1) * rawPitch : 0) + (step < 0 ? span - 1 : 0);
+        CU_TRY(ssimk::launch_pack_u8(s, dst, (long long)canonPitch, d0, step, stride < 0 ? -(long long)rawPitch : (long long)rawPitch, (int)W, (int)H));
+    } else {
+        const size_t bytes = (size_t)(hi - lo) + 1;
+        if ((rc = rawBuf.ensure(bytes))) return rc;
+        CU_TRY(cudaMemcpyAsync(rawBuf.ptr, img + lo, bytes, cudaMemcpyHostToDevice, s));
+        CU_TRY(ssimk::launch_pack_u8(s, dst, (long long)canonPitch, (const uint8_t*)rawBuf.ptr - lo, step, stride, (int)W, (int)H));
+    }
+    return 0;
+}
+
+// One "general job" = one image pair (or one row strip of it) in the caller's layout, enqueued on the context's
+// stream: inputs are made canonical, the fused kernel runs, the map starts flowing back.  finish_general() waits
+// and completes the host-side part.  `a`/`b` point at source row 0 of the strip, `map` at its first OUTPUT row.
+struct GeneralJob {
+    Context* c = nullptr;
+    uint32_t W = 0, outRows = 0;
+    float* map = nullptr;
+    ptrdiff_t mapStep = 0, mapStride = 0;
+    bool cpuScatter = false;
+};
+
+int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, uint32_t outRows, const uint8_t* a, ptrdiff_t stepA,
+                    ptrdiff_t strideA, const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep,
+                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job)
+{
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint8_t *pa, *pb;
+    size_t pitchA, pitchB;
+    int rc;
+    if ((rc = canonical_plane(c, s, a, stepA, strideA, W, srcRows, c->planeA, c->rawA, &pa, &pitchA))) return rc;
+    if ((rc = canonical_plane(c, s, b, stepB, strideB, W, srcRows, c->planeB, c->rawB, &pb, &pitchB))) return rc;
+
+    // map destination: write straight into a canonical device map of the caller, else into scratch
+    float* dMap = nullptr;
+    size_t dMapPitch = 0;
+    bool mapDirect = false;
+    Where mapWhere = Where::Host;
+    if (map) {
+        mapWhere = classify(map);
+        if (mapWhere == Where::Device && mapStep == 1 && mapStride >= (ptrdiff_t)W) {
+            dMap = map; dMapPitch = (size_t)mapStride; mapDirect = true;
+        } else {
+            dMapPitch = align_up(W, 4);
+            if ((rc = c->map.ensure(dMapPitch * outRows * sizeof(float)))) return rc;
+            dMap = (float*)c->map.ptr;
+        }
+    }
+    if ((rc = c->scalars.ensure(16))) return rc;
+    double* dSum = (double*)c->scalars.ptr;
+    float* dSsim = (float*)((char*)c->scalars.ptr + 8);
+
+    rc = compute_device_impl(c, s, W, srcRows, outY0, outRows, 1, pa, pitchA, 0, pb, pitchB, 0, dMap, dMapPitch, 0, dSum,
+                             wantSsim ? dSsim : nullptr);
+    if (rc) return rc;
+
+    job->c = c; job->W = W; job->outRows = outRows; job->map = map; job->mapStep = mapStep; job->mapStride = mapStride;
+    job->cpuScatter = false;
+    if (map && !mapDirect) {
+        if (mapWhere == Where::Device) {
+            CU_TRY(ssimk::launch_scatter_map(s, map, mapStep, mapStride, dMap, (long long)dMapPitch, (int)W, (int)outRows));
+        } else if (mapStep == 1 && mapStride >= (ptrdiff_t)W) {
+            CU_TRY(cudaMemcpy2DAsync(map, (size_t)mapStride * sizeof(float), dMap, dMapPitch * sizeof(float), (size_t)W * sizeof(float),
+                                     outRows, cudaMemcpyDeviceToHost, s));
+        } else {
+            // strided / bottom-up host map: dense copy to pinned staging, scattered by the CPU in finish_general(),
+            // touching only the addressed floats (interleaved neighbours stay untouched, as in src/ssim.cpp:661-667)
+            if ((rc = c->stage.ensure((size_t)W * outRows * sizeof(float)))) return rc;
+            CU_TRY(cudaMemcpy2DAsync(c->stage.ptr, (size_t)W * sizeof(float), dMap, dMapPitch * sizeof(float), (size_t)W * sizeof(float),
+                                     outRows, cudaMemcpyDeviceToHost, s));
+            job->cpuScatter = true;
+        }
+    }
+    return 0;
+}
+
+int finish_general(const GeneralJob& job)
+{
+    CU_TRY(cudaSetDevice(job.c->device));
+    CU_TRY(cudaStreamSynchronize(job.c->stream));
+    if (job.cpuScatter) {
+        const float* src = (const float*)job.c->stage.ptr;
+        for (uint32_t y = 0; y < job.outRows; ++y)
+            for (uint32_t x = 0; x < job.W; ++x)
+                job.map[(ptrdiff_t)x * job.mapStep + (ptrdiff_t)y * job.mapStride] = src[(size_t)y * job.W + x];
+    }
+    return 0;
+}
+
+int compute_general(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA, const uint8_t* b,
+                    ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
+{
+    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    GeneralJob job;
+    int rc = enqueue_general(c, W, H, 0, H, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job);
+    if (rc) return rc;
+    float hostSsim = 0.f;
+    if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = finish_general(job))) return rc;
+    if (ssim) *ssim = hostSsim;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen'ed)
+// Only the scalar partial sums cross GPUs (BASELINE.json north_star), so NCCL is loaded lazily and privately:
+// libssim_cuda.so has no link-time dependency on it and coexists with a framework that bundles its own copy.
+struct Nccl {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::map<std::vector<int>, std::vector<ncclComm_t>> comms;
+    std::mutex mutex;
+};
+Nccl g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.handle) return 0;
+    const char* names[] = {getenv("SSIM_CUDA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n) continue;
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return fail(EIO, "cannot load NCCL (libnccl.so.2): %s", dlerror());
+#define NCCL_SYM(field, name)                                                                  \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.handle, name);                                     \
+    if (!g_nccl.field) return fail(EIO, "NCCL symbol %s not found", name);
+    NCCL_SYM(CommInitAll, "ncclCommInitAll")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(AllReduce, "ncclAllReduce")
+    NCCL_SYM(GroupStart, "ncclGroupStart")
+    NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    return 0;
+}
+
+#define NCCL_TRY(expr)                                                                          \
+    do {                                                                                        \
+        ncclResult_t r__ = (expr);                                                              \
+        if (r__ != ncclSuccess) return fail(EIO, "%s: %s", #expr, g_nccl.GetErrorString(r__));  \
+    } while (0)
+
+int compute_strips(int n, const int* devices, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                   const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
+{
+    std::vector<Context*> ctx(n);
+    for (int g = 0; g < n; ++g) {
+        for (int k = 0; k < g; ++k)
+            if (devices[k] == devices[g]) return fail(EINVAL, "device %d listed twice", devices[g]);
+        int rc = get_context(devices[g], &ctx[g]);
+        if (rc) return rc;
+    }
+    std::vector<ncclComm_t>* comms = nullptr;
+    if (n > 1) {
+        std::lock_guard<std::mutex> lock(g_nccl.mutex);
+        int rc = nccl_load();
+        if (rc) return rc;
+        std::vector<int> key(devices, devices + n);
+        auto it = g_nccl.comms.find(key);
+        if (it == g_nccl.comms.end()) {
+            std::vector<ncclComm_t> c(n);
+            NCCL_TRY(g_nccl.CommInitAll(c.data(), n, devices));
+            it = g_nccl.comms.emplace(key, c).first;
+        }
+        comms = &it->second;
+    }
+    // lock the contexts in device order (no lock-order inversion between concurrent callers)
+    std::vector<int> order(n);
+    for (int g = 0; g < n; ++g) order[g] = g;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return devices[x] < devices[y]; });
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int g : order) locks.emplace_back(ctx[g]->hostPathMutex);
+
+    // strip g produces rows [g*H/n, (g+1)*H/n) and reads 5 more rows on each interior edge (src/ssim.cpp:749-761:
+    // every tile of the reference re-reads its halo the same way)
+    std::vector<GeneralJob> jobs(n);
+    std::vector<bool> active(n, false);
+    for (int g = 0; g < n; ++g) {
+        const uint32_t y0 = (uint32_t)((uint64_t)H * g / n), y1 = (uint32_t)((uint64_t)H * (g + 1) / n);
+        CU_TRY(cudaSetDevice(devices[g]));
+        int rc = ctx[g]->scalars.ensure(16);
+        if (rc) return rc;
+        if (y1 == y0) { CU_TRY(cudaMemsetAsync(ctx[g]->scalars.ptr, 0, 16, ctx[g]->stream)); continue; }
+        const uint32_t s0 = y0 >= (uint32_t)ssimk::kHalo ? y0 - ssimk::kHalo : 0, s1 = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
+        rc = enqueue_general(ctx[g], W, s1 - s0, y0 - s0, y1 - y0, a + (ptrdiff_t)s0 * strideA, stepA, strideA, b + (ptrdiff_t)s0 * strideB,
+                             stepB, strideB, map ? map + (ptrdiff_t)y0 * mapStride : nullptr, mapStep, mapStride, false, &jobs[g]);
+        if (rc) return rc;
+        active[g] = true;
+    }
+    if (n > 1) {
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int g = 0; g < n; ++g)
+            NCCL_TRY(g_nccl.AllReduce(ctx[g]->scalars.ptr, ctx[g]->scalars.ptr, 1, ncclDouble, ncclSum, (*comms)[g], ctx[g]->stream));
+        NCCL_TRY(g_nccl.GroupEnd());
+    }
+    double total = 0.0;
+    CU_TRY(cudaSetDevice(devices[0]));
+    CU_TRY(cudaMemcpyAsync(&total, ctx[0]->scalars.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx[0]->stream));
+    for (int g = 0; g < n; ++g) {
+        if (active[g]) { int rc = finish_general(jobs[g]); if (rc) return rc; }
+        else { CU_TRY(cudaSetDevice(devices[g])); CU_TRY(cudaStreamSynchronize(ctx[g]->stream)); }
+    }
+    if (ssim) *ssim = (float)(total / (double)(uint32_t)(W * H));
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int ssim_cuda_abi_version(void) { return SSIM_CUDA_ABI_VERSION; }
+
+int ssim_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ssim_cuda_init(int device)
+{
+    Context* c;
+    return get_context(device, &c);
+}
+
+void ssim_cuda_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    for (auto& kv : g_ctx) {
+        Context* c = kv.second;
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (Buffer* b : {&c->planeA, &c->planeB, &c->rawA, &c->rawB, &c->map, &c->stage, &c->scalars}) b->release();
+        for (auto& p : c->partials) p.second.release();
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+    }
+    g_ctx.clear();
+    {
+        std::lock_guard<std::mutex> nlock(g_nccl.mutex);
+        for (auto& kv : g_nccl.comms)
+            for (ncclComm_t comm : kv.second) g_nccl.CommDestroy(comm);
+        g_nccl.comms.clear();
+    }
+}
+
+const char* ssim_cuda_last_error_string(void) { return g_err; }
+
+void* ssim_cuda_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void ssim_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int ssim_cuda_compute(int device, uint32_t width, uint32_t height, const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                      const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
+{
+    if (ssim == nullptr && map == nullptr) return fail(EINVAL, "both ssim and map are NULL, nothing would be computed");
+    if (a == nullptr || b == nullptr) return fail(EINVAL, "image pointer is NULL");
+    if (width == 0 || height == 0) return fail(EINVAL, "width and height must be non-zero");
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    return compute_general(c, width, height, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim);
+}
+
+int ssim_cuda_compute_device(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,
+                             const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB, size_t frameStrideB,
+                             float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim)
+{
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, frames, dA, pitchA, frameStrideA, dB, pitchB,
+                               frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim);
+}
+
+int ssim_cuda_last_launch_count(void) { return g_lastLaunches; }
+
+int ssim_cuda_compute_strips(int nDevices, const int* devices, uint32_t width, uint32_t height, const uint8_t* a, ptrdiff_t stepA,
+                             ptrdiff_t strideA, const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep,
+                             ptrdiff_t mapStride, float* ssim)
+{
+    if (nDevices < 1 || nDevices > 64 || devices == nullptr) return fail(EINVAL, "bad device list");
+    if (ssim == nullptr && map == nullptr) return fail(EINVAL, "both ssim and map are NULL, nothing would be computed");
+    if (a == nullptr || b == nullptr) return fail(EINVAL, "image pointer is NULL");
+    if (width == 0 || height == 0) return fail(EINVAL, "width and height must be non-zero");
+    return compute_strips(nDevices, devices, width, height, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim);
+}
+
+int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, uint8_t* dB, size_t pitchB, uint32_t width, uint32_t rows,
+                         uint32_t y0, uint32_t frame, uint64_t seed)
+{
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    if (!dA || !dB || width == 0 || rows == 0) return fail(EINVAL, "bad synth_fill arguments");
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(ssimk::launch_synth_fill((cudaStream_t)stream, dA, (long long)pitchA, dB, (long long)pitchB, (int)width, (int)rows, (int)y0, frame, seed));
+    return 0;
+}
+
+void ssim_cuda_set_segment_rows(int rows) { g_segRowsOverride = rows > 0 ? rows : 0; }
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// ssim_kernels.h -- launch interface between the runtime (ssim_cuda.cu) and the sm_100a kernels.
+#ifndef SSIM_B200_KERNELS_H
+#define SSIM_B200_KERNELS_H
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ssimk {
+
+// ---- geometry of the fused kernel (see DESIGN.md "Kernel")
+constexpr int kBandW       = 64;   // output columns per warp work item (lane owns columns lane and lane+32)
+constexpr int kBlkRows     = 8;    // rows per TMA block / horizontal-pass block
+constexpr int kHalo        = 5;    // Gaussian radius (reference src/ssim.cpp:227)
+constexpr int kBoxW        = 128;  // TMA box width in bytes: 16 left margin + 64 columns + right margin; 128 so that every box
+                                   // row (and so every single-row edge load) lands on a 128-byte aligned shared-memory address
+constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row: the innermost TMA coordinate (bx - 16) must be
+                                   // a multiple of 16 bytes -- measured on B200: x = -16 works, x = -8 raises "illegal instruction"
+                                   // (tools/dev/tma_probe.cu)
+constexpr int kStages      = 3;    // TMA ring depth per warp
+constexpr int kWarpsPerCta = 4;
+constexpr int kImgStageBytes = kBoxW * kBlkRows;         // 1024
+constexpr int kStageBytes    = 2 * kImgStageBytes;       // 2048 (A then B)
+constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
+constexpr int kRingRowBytes   = 2 * kRingPlaneBytes;     // 1024: {E[a'], E[b']} plane then {E[(a'-b')^2], E[a'b']} plane
+constexpr int kRingBytes      = kBlkRows * kRingRowBytes; // 8192: horizontal-pass output of one block
+constexpr int kWarpSmemBytes = kStages * kStageBytes + kRingBytes;  // 14336
+constexpr int kCtaSmemBytes  = kWarpsPerCta * kWarpSmemBytes;       // 57344
+
+struct FusedParams {
+    const uint8_t* a;        // raw planes (used only to fetch the per-item centring pixel)
+    const uint8_t* b;
+    long long pitchA, frameStrideA, pitchB, frameStrideB;
+    float*  map;             // NULL when no map is wanted
+    long long mapPitch, mapFrameStride;   // floats
+    double* partials;        // [items] per-warp-item partial sums
+    int width, srcRows, outY0, outRows, frames;
+    int bands, segs, segRows;
+    long long items;
+    float g[6];              // separable 11-tap weights: g[d] is the tap at distance d from the centre
+    float c1, c2;
+    float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
+};
+
+struct FinalizeParams {
+    const double* partials;
+    double* sums;            // may be NULL
+    float*  ssim;            // may be NULL
+    int itemsPerFrame;
+    double invCount;         // 1 / double(uint32(width*outRows))
+};
+
+cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA8, const CUtensorMap& tmA1,
+                         const CUtensorMap& tmB8, const CUtensorMap& tmB1, const FusedParams& p);
+cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames);
+cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm);
+
+// layout helpers
+cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
+                           long long step, long long stride, int width, int height);
+cudaError_t launch_scatter_map(cudaStream_t stream, float* dst, long long dstStep, long long dstStride,
+                               const float* src, long long srcPitch, int width, int height);
+cudaError_t launch_synth_fill(cudaStream_t stream, uint8_t* dA, long long pitchA, uint8_t* dB, long long pitchB,
+                              int width, int rows, int y0, uint32_t frame, uint64_t seed);
+
+}  // namespace ssimk
+#endif

@@ -1,0 +1,173 @@
+"""GPU parity tests: the CUDA path, called through the reference-facing C ABI (rmgr_ssim_compute_ssim in
+librmgr-ssim.so -> ssim_cuda_compute in libssim_cuda.so), against the CPU oracle on identical inputs.
+
+Gate (BASELINE.json north_star; reference tests/rmgr-ssim-tests.cpp:98-104):
+    |global - O1| <= 2e-6   and   max |map - O1 map| <= 1e-3
+where O1 is the reference's RMGR_SSIM_USE_DOUBLE build with default dispatch -- reproduced bit-for-bit on the
+map by oracle.oracle_ssim(taps=TAPS_TABLE) (tests/test_oracle.py) and, when oracle/_ref is present, run live."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GLOBAL_TOL, PIXEL_TOL
+from ssim_b200 import api
+from ssim_b200.synth import synth_pair
+
+pytestmark = pytest.mark.gpu
+
+EINSTEIN = ["einstein", "meanshift", "contrast", "impulse", "blur", "jpg"]
+ERRS = []
+
+
+def _report(tag, s, o, m=None, om=None):
+    dg = abs(float(s) - float(o))
+    line = "%-28s global %.9f  oracle %.9f  |d| %.2e" % (tag, s, o, dg)
+    if m is not None:
+        d = np.abs(m.astype(np.float64) - om.astype(np.float64))
+        line += "   map max %.2e  p99.9 %.2e  mean %.2e" % (d.max(), np.quantile(d, 0.999), d.mean())
+    ERRS.append(line)
+    print(line)
+    return dg
+
+
+def _check_pair(tag, a, b, **kw):
+    s, m = api.compute_ssim(a, b, want_map=True, **kw)
+    okw = {k: v for k, v in kw.items() if k in ("width", "height", "step_a", "step_b", "stride_a", "stride_b", "a_off", "b_off")}
+    o, _, om = oracle.oracle_ssim(a, b, want_map=True, taps=oracle.TAPS_TABLE, **okw)
+    dg = _report(tag, s, o, m, om)
+    assert dg <= GLOBAL_TOL
+    assert np.abs(m - om).max() <= PIXEL_TOL
+    # no-map call must give the same global value
+    s2, _ = api.compute_ssim(a, b, want_map=False, **kw)
+    assert s2 == s
+    return s, m
+
+
+def test_library_loads_and_reports_version():
+    assert api.get_version() == (2, 1, 0, "2.1.0")
+    assert api.cuda_lib().ssim_cuda_device_count() >= 1
+
+
+@pytest.mark.parametrize("name", EINSTEIN)
+def test_einstein(name, einstein, golden):
+    """BASELINE.json configs[0]: the tests/images pair set, 256x256 gray, global SSIM + map"""
+    s, m = _check_pair("einstein/" + name, einstein[name], einstein["einstein"])
+    # the reference's own known answers (tests/rmgr-ssim-tests.cpp:354-359) at its float tolerance
+    assert abs(float(s) - float(golden["einstein"][name]["golden_double_mean"])) <= GLOBAL_TOL
+    if name == "einstein":
+        assert s == np.float32(1.0) and (m == 1.0).all()       # identical images give exactly 1
+
+
+@pytest.mark.parametrize("dims", [(1, 1), (2, 3), (7, 3), (5, 5), (11, 11), (16, 16), (255, 63), (256, 64), (257, 65), (300, 1),
+                                  (1, 300), (513, 129), (64, 75), (65, 11), (130, 200), (63, 8), (59, 6), (69, 20), (70, 9), (128, 3)])
+def test_edge_dims(dims):
+    w, h = dims
+    a, b = synth_pair(w, h, 3)
+    _check_pair("synthetic %dx%d" % dims, a, b)
+    rng = np.random.default_rng(w * 7919 + h)
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    b = np.clip(a.astype(np.int32) + rng.integers(-25, 26, (h, w)), 0, 255).astype(np.uint8)
+    _check_pair("random %dx%d" % dims, a, b)
+
+
+@pytest.mark.parametrize("dims", [(255, 63), (257, 65), (640, 80)])
+def test_bbb_interleaved_crops(dims, bbb360):
+    """step = 3, stride != width*step (reference tests :388-465)"""
+    w, h = dims
+    for ch in range(3):
+        _check_pair("bbb360 %dx%d ch%d" % (w, h, ch), bbb360["jpg50"], bbb360["png"], width=w, height=h, step_a=3, step_b=3,
+                    stride_a=640 * 3, stride_b=640 * 3, a_off=ch, b_off=ch)
+
+
+def test_synthetic_1080p_and_4k(golden):
+    """BASELINE.json configs[1] (1080p, global only) and configs[2] (4K with map)"""
+    a, b = synth_pair(1920, 1080, 0)
+    s, _ = api.compute_ssim(a, b)
+    g = golden["synthetic"]["1920x1080_f0"]
+    _report("synthetic 1080p f0 (vs O1)", s, g["ref_f64_auto"])
+    _report("synthetic 1080p f0 (vs O2)", s, g["ref_f64_generic"])
+    assert abs(float(s) - g["ref_f64_auto"]) <= GLOBAL_TOL
+    _check_pair("synthetic 1080p f0", a, b)
+    a, b = synth_pair(3840, 2160, 0)
+    s, m = api.compute_ssim(a, b, want_map=True)
+    g = golden["synthetic"]["3840x2160_f0"]
+    _report("synthetic 4K f0 (vs O1)", s, g["ref_f64_auto"])
+    assert abs(float(s) - g["ref_f64_auto"]) <= GLOBAL_TOL
+    if oracle.have_ref():
+        r, rm = oracle.ref_ssim("f64", a, b, want_map=True, openmp=True)
+        _report("synthetic 4K f0 live O1", s, r, m, rm)
+        assert np.abs(m - rm).max() <= PIXEL_TOL
+
+
+def test_negative_strides_flip_and_map_layouts():
+    a, b = synth_pair(97, 41, 5)
+    s, m = api.compute_ssim(a, b, want_map=True)
+    n = a.size
+    # bottom-up images, bottom-up map with a step of 2 floats: interleaved slots must stay untouched
+    buf = np.full((41, 97 * 2), -7.0, dtype=np.float32)
+    sf, _ = api.compute_ssim(a, b, width=97, height=41, stride_a=-97, stride_b=-97, a_off=n - 97, b_off=n - 97,
+                             ssim_map=buf, map_step=2, map_stride=-97 * 2, map_off=40 * 97 * 2)
+    assert abs(float(s) - float(sf)) <= 1e-6
+    # image row y was read bottom-up => output row y is image row 40-y; map written bottom-up => row 40-y of buf... = same row
+    assert np.allclose(buf[:, 0::2], m, atol=2e-4) and (buf[:, 1::2] == -7.0).all()
+    # column-major traversal (swap step/stride and width/height) gives the transposed map and the same global value
+    st, mt = api.compute_ssim(a, b, want_map=True, width=41, height=97, step_a=97, step_b=97, stride_a=1, stride_b=1)
+    assert abs(float(s) - float(st)) <= 1e-6 and np.allclose(mt, m.T, atol=2e-4)
+
+
+def test_map_only_and_errors():
+    a, b = synth_pair(70, 20, 1)
+    s, m = api.compute_ssim(a, b, want_map=True)
+    _, m2 = api.compute_ssim(a, b, want_map=True, want_ssim=False)
+    assert np.array_equal(m, m2)
+    lib = api.rmgr_lib()
+    out = C.c_float()
+    p = api.make_params(a, b, 70, 20)
+    assert lib.rmgr_ssim_compute_ssim(None, C.byref(p), None) == 22                      # both outputs NULL
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), None, None) == 22                    # params NULL
+    p.imgA.topLeft = None
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 22              # NULL image
+    p = api.make_params(a, b, 0, 20)
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 22              # empty image (documented divergence)
+    tp = api.ThreadPool()
+    tp.dispatch = C.cast(C.CFUNCTYPE(C.c_int)(lambda: 0), C.c_void_p)
+    tp.threadCount = 0
+    p = api.make_params(a, b, 70, 20)
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), C.byref(tp)) == 22       # dispatch with 0 threads
+    tp.threadCount = 4
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), C.byref(tp)) == 0        # pool accepted, not used
+    assert abs(out.value - float(s)) == 0
+    assert lib.rmgr_ssim_compute_ssim_openmp(C.byref(out), C.byref(p)) == 0 and out.value == float(s)
+
+
+def test_flat_and_extreme_images():
+    """constant images (fp32 cancellation worst case) and full-range noise"""
+    for va, vb in [(0, 0), (255, 255), (200, 199), (0, 255), (17, 230)]:
+        a = np.full((40, 150), va, np.uint8)
+        b = np.full((40, 150), vb, np.uint8)
+        s, m = api.compute_ssim(a, b, want_map=True)
+        o, _, om = oracle.oracle_ssim(a, b, want_map=True, taps=oracle.TAPS_TABLE)
+        dg = _report("flat %d/%d" % (va, vb), s, o, m, om)
+        assert dg <= GLOBAL_TOL and np.abs(m - om).max() <= PIXEL_TOL
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (90, 333), dtype=np.uint8)
+    b = rng.integers(0, 256, (90, 333), dtype=np.uint8)
+    _check_pair("independent noise", a, b)
+
+
+def test_determinism():
+    a, b = synth_pair(1000, 700, 9)
+    s1, m1 = api.compute_ssim(a, b, want_map=True)
+    s2, m2 = api.compute_ssim(a, b, want_map=True)
+    assert s1 == s2 and np.array_equal(m1, m2)
+
+
+def test_zz_error_report():
+    """prints the collected error distributions (kept in gpurun_out/parity_errors.txt by the driver script)"""
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_errors.txt"), "w") as fh:
+        fh.write("\n".join(ERRS) + "\n")
