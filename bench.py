@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: SSIM Mpix/s (device-timed), 3840x2160 8-bit pairs WITH per-pixel map.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's own FMA+OpenMP CPU path, oracle/_ref)
+
+A "step" is one pass of the hot path over one batch: FRAMES synthetic 4K frame pairs per GPU (SURVEY.md 8(d)
+recipe, seed 0x5517, resident in HBM before the timed region), one ssim_cuda_compute_device() call = one fused
+kernel launch + one tiny reduction launch, producing FRAMES maps and FRAMES global SSIM values.  Frames are
+independent, so with N GPUs each rank owns its own FRAMES frames and there is no data-path collective (weak
+scaling); the timed region is bracketed by barrier + synchronize and the slowest rank's device time counts.
+
+Printed JSON (one line, rank 0):
+  value      whole-job Mpix/s (all ranks' pixels / max-over-ranks device time), inputs and outputs in HBM
+  e2e        same metric through the reference-facing API rmgr_ssim_compute_ssim() with pinned HOST buffers:
+             H2D of both images and D2H of the map + scalar inside the timed region, one blocking call per frame
+  roofline   the fused kernel alone (CUDA events around K launches with no reduction kernel): algorithmic
+             230 flop/pixel / duration vs the FP32 FFMA peak 148 SM x 128 lanes x 2 x sm_max_mhz
+             (MEASURED_PEAKS.json has no FP32 figure; tools/microbench measured 97-99% of this nominal peak),
+             plus the HBM view (6 B/pixel with map vs the measured copy bandwidth)
+  cpu_baseline  the UNMODIFIED reference (float build, AUTO dispatch = FMA blur, OpenMP over all host cores),
+             compiled from /root/reference into oracle/_ref, timed on a bounded sample of the same frames
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 3840, 2160
+FRAMES = 64                      # 4K pairs per GPU per step: 1.06 GB of inputs + 2.1 GB of maps (>> 126 MB L2)
+FLOP_PER_PIXEL = 230.0           # algorithmic work of the separable formulation
+BYTES_PER_PIXEL_MAP = 6.0        # 2 B read + 4 B map write
+METRIC = "ssim_mpix_per_s_4k_with_map"
+UNIT = "Mpix/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), float(p["sm_max_mhz"]), "measured"
+    return 6650.0, 1965.0, "fallback"          # B200_PROFILING.md fallback
+
+
+def config(args, n):
+    return {"workload": "3840x2160 8-bit grayscale pairs with per-pixel map (BASELINE.json configs[2]), %d pairs per GPU per step" % args.frames,
+            "frames_per_gpu_per_step": args.frames, "width": W, "height": H,
+            "l2": "per-step working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (args.frames * W * H * 6 / 1e9),
+            "parallelism": "frames sharded one batch per GPU (dp%d), no data-path collective" % n}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def time_reference(frames_host, seconds=None, steps=None, warmup=1):
+    """Runs the unmodified reference (oracle/_ref/libref_f32.so, rmgr_ssim_compute_ssim_openmp) on host frames.
+    Either for ~`seconds` of wall clock or for `steps` timed steps of len(frames_host) frames each."""
+    import numpy as np
+
+    import oracle
+    from ssim_b200._abi import make_params
+    lib = oracle.ref_lib("f32")
+    lib.ref_select_impl(oracle.IMPL_AUTO)
+    cores = min(os.cpu_count() or 1, 64)          # reference caps threads at 64 (src/ssim.cpp:1025-1029)
+    m = np.empty((H, W), dtype=np.float32)
+    out = C.c_float()
+
+    def one(a, b):
+        p = make_params(a, b, W, H, ssim_map=m)
+        rc = lib.rmgr_ssim_compute_ssim_openmp(C.byref(out), C.byref(p))
+        assert rc == 0, rc
+
+    for _ in range(warmup):
+        for a, b in frames_host:
+            one(a, b)
+    done = 0
+    t0 = time.perf_counter()
+    if steps is not None:
+        for _ in range(steps):
+            for a, b in frames_host:
+                one(a, b)
+                done += 1
+    else:
+        while time.perf_counter() - t0 < seconds or done < 3:
+            a, b = frames_host[done % len(frames_host)]
+            one(a, b)
+            done += 1
+    dt = time.perf_counter() - t0
+    return done * W * H / dt / 1e6, cores, done, dt, float(out.value)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from ssim_b200.synth import synth_pair
+    n = args.gpus
+    if not oracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    sample = 2                                     # frames per step: bounded sample of the 64-frame batch
+    frames = [synth_pair(W, H, f) for f in range(sample)]
+    mpix, cores, done, dt, _ = time_reference(frames, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": round(mpix, 2), "unit": UNIT, "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args, n),
+            "cpu_baseline": {"value": round(mpix, 2), "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "%d synthetic 4K pairs with map per step (frames 0..%d), %d steps, rmgr_ssim_compute_ssim_openmp of the unmodified float build" % (sample, sample - 1, args.steps)},
+            "e2e": {"value": round(mpix, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML every ~5 ms while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ssim_b200 import api
+
+    n = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == n, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (n, world)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = api.cuda_lib()
+    assert lib.ssim_cuda_device_count() > local, "no CUDA device: ssim_b200 has no CPU fallback"
+    dev = torch.device("cuda", local)
+    F = args.frames
+    npx = W * H
+
+    # ---- inputs resident in HBM: frames rank*F .. rank*F+F-1 of the synthetic sweep
+    dA = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
+    dB = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
+    dMap = torch.empty((F, H, W), dtype=torch.float32, device=dev)
+    dSums = torch.empty(F, dtype=torch.float64, device=dev)
+    dSsim = torch.empty(F, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    for f in range(F):
+        api.synth_fill(local, sh, dA[f].data_ptr(), W, dB[f].data_ptr(), W, W, H, 0, rank * F + f)
+    torch.cuda.synchronize()
+
+    def step(with_reduce=True):
+        api.compute_device(local, sh, W, H, 0, H, F, dA.data_ptr(), W, npx, dB.data_ptr(), W, npx, dMap.data_ptr(), W, npx,
+                           dSums.data_ptr() if with_reduce else None, dSsim.data_ptr() if with_reduce else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- device-timed whole-job throughput
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = args.steps * lib.ssim_cuda_last_launch_count()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n * F * npx * args.steps / (ms_max * 1e-3) / 1e6
+    ssim_first = float(dSsim[0].item())
+
+    # ---- roofline: the fused kernel alone (no reduction launch), CUDA events on the launching stream
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for _ in range(args.steps):
+        step(with_reduce=False)
+    k1.record(stream)
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+
+    # ---- one 4K pair per launch (latency view; BASELINE.md: <= 42.7 us is the 60% target)
+    single = []
+    for i in range(3 + 20):
+        f = i % F
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        api.compute_device(local, sh, W, H, 0, H, 1, dA[f].data_ptr(), W, npx, dB[f].data_ptr(), W, npx, dMap[f].data_ptr(), W, npx,
+                           dSums.data_ptr(), dSsim.data_ptr())
+        s1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 3:
+            single.append(s0.elapsed_time(s1) * 1e3)
+
+    # ---- end to end through the reference-facing API with pinned host buffers (H2D + D2H inside the timed region)
+    eF = min(F, 8)                                     # host frames kept pinned (rotated), 8 x 50 MB
+    hA = torch.empty((eF, H, W), dtype=torch.uint8).pin_memory()
+    hB = torch.empty((eF, H, W), dtype=torch.uint8).pin_memory()
+    hMap = torch.empty((eF, H, W), dtype=torch.float32).pin_memory()
+    hA.copy_(dA[:eF])
+    hB.copy_(dB[:eF])
+    torch.cuda.synchronize()
+    nA, nB, nM = hA.numpy(), hB.numpy(), hMap.numpy()
+    os.environ["SSIM_CUDA_DEVICE"] = str(local)
+
+    def e2e_step():
+        last = None
+        for f in range(F):
+            k = f % eF
+            last, _ = api.compute_ssim(nA[k], nB[k], ssim_map=nM[k])
+        return last
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(1):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_last = e2e_step()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    td = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    e2e_value = n * F * npx * e2e_steps / float(td.item()) / 1e6
+
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_gbs, sm_max_mhz, peak_kind = peaks()
+    fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # TFLOP/s
+    achieved = FLOP_PER_PIXEL * F * npx / (kernel_ms * 1e-3) / 1e12
+    hbm_achieved = BYTES_PER_PIXEL_MAP * F * npx / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "fused_kernel_dram_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if tj.get("frames") == F:
+            traffic = tj.get("dram_bytes_per_launch")
+
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args, n),
+            "clocks": sampler.summary(),
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": F * 2 * npx, "d2h_bytes_per_step": F * (npx * 4 + 4),
+                    "api": "rmgr_ssim_compute_ssim (librmgr-ssim.so), one blocking call per 4K pair, pinned host buffers", "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "achieved": round(achieved, 2), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+                         "frac": round(achieved / fp32_peak, 4), "traffic": traffic,
+                         "kernel": "ssim_fused_kernel<true>", "kernel_ms_per_launch": round(kernel_ms, 4),
+                         "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json sm_max_mhz); FFMA microbench reaches 97-99%% of it" % peak_kind,
+                         "hbm": {"achieved": round(hbm_achieved, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(hbm_achieved / hbm_gbs, 4),
+                                 "peak_source": "%s copy bandwidth" % peak_kind}},
+            "single_pair_us": {"median": round(statistics.median(single), 2), "min": round(min(single), 2),
+                               "mpix_per_s_at_median": round(npx / statistics.median(single), 1)},
+            "ssim_frame0": ssim_first, "ssim_e2e_last": float(e2e_last)}
+
+    if n == 1 and not args.no_cpu_baseline:
+        import oracle
+        if oracle.have_ref():
+            frames = [(nA[k], nB[k]) for k in range(min(eF, 4))]
+            mpix, cores, done, cdt, cpu_ssim = time_reference(frames, seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": round(mpix, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": "%d calls of rmgr_ssim_compute_ssim_openmp (unmodified float build, AUTO=FMA dispatch) on synthetic 4K pairs with map, %.1f s" % (done, cdt),
+                                    "ssim_last": cpu_ssim}
+        else:
+            line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -273,9 +273,9 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (rc) return rc;
 
     CUtensorMap tmA8, tmA1, tmB8, tmB1;
-    if ((rc = make_plane_map(&tmA8, dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kBlkRows))) return rc;
+    if ((rc = make_plane_map(&tmA8, dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows))) return rc;
     if ((rc = make_plane_map(&tmA1, dA, width, srcRows, frames, pitchA, frameStrideA, 1))) return rc;
-    if ((rc = make_plane_map(&tmB8, dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kBlkRows))) return rc;
+    if ((rc = make_plane_map(&tmB8, dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows))) return rc;
     if ((rc = make_plane_map(&tmB1, dB, width, srcRows, frames, pitchB, frameStrideB, 1))) return rc;
 
     ssimk::FusedParams p;

@@ -74,7 +74,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // u8 -> f32 without the conversion pipe: PRMT builds the float 2^23 + byte, the packed FADD that follows removes
 // 2^23 + centre (exact).  I2F.U8 runs at 1/8 rate on B200 (tools/microbench), PRMT is an ALU-pipe op.
 template <int kByte>
-__device__ __forceinline__ float magic_byte(uint32_t word) { return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 + kByte)); }
+__device__ __forceinline__ float magic_byte(uint32_t word, uint32_t magic) { return __uint_as_float(__byte_perm(word, magic, 0x7440 + kByte)); }
 
 // ------------------------------------------------------------------------------------------------ fused kernel
 template <bool kMap>
@@ -113,34 +113,35 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     }
     __syncwarp();
 
-    // One TMA block = rows [inY0 + 8*blk, +8) x bytes [bx-16, bx+112) of both images.  Rows outside the plane are
-    // clamped by loading single-row boxes at clamped coordinates (replicates the nearest row, src/ssim.cpp:562-582);
-    // columns outside the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
-    auto issue_block = [&](int blk) {
-        const int stage = blk % kStages;
+    // One TMA load = rows [inY0 + 16*ld, +16) x bytes [bx-16, bx+112) of both images = two 8-row blocks.  Rows outside
+    // the plane are clamped by loading single-row boxes at clamped coordinates (replicates the nearest row,
+    // src/ssim.cpp:562-582); columns outside the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
+    const int nLoads = (nBlk + 1) >> 1;
+    auto issue_load = [&](int ld) {
+        const int stage = ld & (kStages - 1);
         const uint32_t bar = barBase + 8 * stage;
         const uint32_t dst = warpSmem + stage * kStageBytes;
-        const int y = inY0 + blk * kBlkRows;
-        if (lane == 0) mbar_arrive_expect_tx(bar, kStageBytes);
-        __syncwarp();
-        if (y >= 0 && y + kBlkRows <= p.srcRows) {
-            if (lane == 0) {
+        const int y = inY0 + ld * kLoadRows;
+        if (lane == 0) {
+            // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes)
+            mbar_arrive_expect_tx(bar, kStageBytes);
+            if (y >= 0 && y + kLoadRows <= p.srcRows) {
                 tma_load_3d(dst, &tmA8, bx - kBoxLeft, y, frame, bar);
                 tma_load_3d(dst + kImgStageBytes, &tmB8, bx - kBoxLeft, y, frame, bar);
-            }
-        } else if (lane == 0) {
-            // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes)
-            for (int r = 0; r < kBlkRows; ++r) {
-                const int yy = min(max(y + r, 0), p.srcRows - 1);
-                tma_load_3d(dst + r * kBoxW, &tmA1, bx - kBoxLeft, yy, frame, bar);
-                tma_load_3d(dst + kImgStageBytes + r * kBoxW, &tmB1, bx - kBoxLeft, yy, frame, bar);
+            } else {
+                #pragma unroll 1
+                for (int r = 0; r < kLoadRows; ++r) {
+                    const int yy = min(max(y + r, 0), p.srcRows - 1);
+                    tma_load_3d(dst + r * kBoxW, &tmA1, bx - kBoxLeft, yy, frame, bar);
+                    tma_load_3d(dst + kImgStageBytes + r * kBoxW, &tmB1, bx - kBoxLeft, yy, frame, bar);
+                }
             }
         }
     };
 
     #pragma unroll
     for (int s = 0; s < kStages; ++s)
-        if (s < nBlk) issue_block(s);
+        if (s < nLoads) issue_load(s);
 
     // ---- per-item centring pixel: moments are accumulated on (a - ca), (b - cb), which keeps the fp32
     // cancellation in E[x^2] - mu^2 small even on flat regions (DESIGN.md "Numerics").  Any integer works.
@@ -149,7 +150,9 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     const float ca = (float)__ldg(p.a + (long long)frame * p.frameStrideA + (long long)cy * p.pitchA + cx);
     const float cb = (float)__ldg(p.b + (long long)frame * p.frameStrideB + (long long)cy * p.pitchB + cx);
     const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));
-    const u64 dpInit   = pack2(-0.5f * p.eps2 * (ca - cb) * (ca - cb), 0.f);     // see the formula below
+    uint32_t magic;                                    // kept opaque so that it lives in a register and PRMT takes the
+    asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));   // byte selector as its immediate (no per-PRMT selector MOV)
+    const float k2     = -0.5f * p.eps2 * (ca - cb) * (ca - cb);                 // see the formula below
 
     // taps: w[m] multiplies the sample at offset m of an 11-sample window, w[m] = g[|m-5|]
     u64 w2[6];
@@ -180,19 +183,23 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
 
     const bool patchLeft  = (bx == 0);
     const bool patchRight = (bx + kBandW + kHalo > p.width);
-    float* mapRow = nullptr;
-    if (kMap) mapRow = p.map + (long long)frame * p.mapFrameStride + (long long)(oy0 - p.outY0) * p.mapPitch + bx + lane;
+    // running map pointer: row of the output completed by the current input row (starts 10 rows above the segment;
+    // never dereferenced there)
+    float* mapPtr = nullptr;
+    if (kMap) mapPtr = p.map + (long long)frame * p.mapFrameStride + (long long)(oy0 - p.outY0 - 2 * kHalo) * p.mapPitch + bx + lane;
 
     double total = 0.0;
 
+    #pragma unroll 1
     for (int blk = 0; blk < nBlk; ++blk) {
-        const int stage = blk % kStages;
-        const uint32_t stageBase = warpSmem + stage * kStageBytes;
-        mbar_wait(barBase + 8 * stage, (uint32_t)(blk / kStages) & 1u);
+        const int ld = blk >> 1, half = blk & 1;                        // TMA load and which 8 of its 16 rows
+        const uint32_t loadBase  = warpSmem + (ld & (kStages - 1)) * kStageBytes;
+        const uint32_t stageBase = loadBase + half * (kBlkRows * kBoxW);
 
-        if (patchLeft || patchRight) {                       // warp-uniform; only the outermost bands
-            if (lane < 2 * kBlkRows) {
-                const uint32_t row = stageBase + (lane >> 3) * kImgStageBytes + (lane & 7) * kBoxW;
+        if (half == 0) {
+            mbar_wait(barBase + 8 * (ld & (kStages - 1)), (uint32_t)(ld / kStages) & 1u);
+            if (patchLeft || patchRight) {                   // warp-uniform; only the outermost bands
+                const uint32_t row = loadBase + (lane >> 4) * kImgStageBytes + (lane & 15) * kBoxW;   // 2 images x 16 rows
                 if (patchLeft) {
                     uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row + kBoxLeft));
                     #pragma unroll
@@ -202,11 +209,10 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
                     const uint32_t last = row + kBoxLeft + (p.width - 1 - bx);
                     uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(last));
                     #pragma unroll
-                    for (int k = 1; k <= kHalo; ++k)
-                        if (kBoxLeft + (p.width - 1 - bx) + k < kBoxW) asm volatile("st.shared.u8 [%0], %1;" :: "r"(last + k), "r"(v) : "memory");
+                    for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(last + k), "r"(v) : "memory");
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         // ================================================================ horizontal pass: 8 rows x 64 columns
@@ -218,11 +224,11 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
             const uint4 b1 = lds128(stageBase + kImgStageBytes + hSrcOff + 8);
             const uint32_t wa[8] = {a0.x, a0.y, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
             const uint32_t wb[8] = {b0.x, b0.y, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-            // every lane has read its inputs once the warp reconverges: the stage can be refilled
+            // every lane has read its inputs once the warp reconverges: after the second half the stage can be refilled
             __syncwarp();
-            if (blk + kStages < nBlk) {
+            if ((half == 1 || blk + 1 >= nBlk) && ld + kStages < nLoads) {
                 if (patchLeft || patchRight) fence_proxy_async();
-                issue_block(blk + kStages);
+                issue_load(ld + kStages);
             }
 
             u64 hab[16], hsp[16];
@@ -231,15 +237,15 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
                 const int byteIdx = i + 3;
                 float fa, fb;
                 switch (byteIdx & 3) {
-                    case 0:  fa = magic_byte<0>(wa[byteIdx >> 2]); fb = magic_byte<0>(wb[byteIdx >> 2]); break;
-                    case 1:  fa = magic_byte<1>(wa[byteIdx >> 2]); fb = magic_byte<1>(wb[byteIdx >> 2]); break;
-                    case 2:  fa = magic_byte<2>(wa[byteIdx >> 2]); fb = magic_byte<2>(wb[byteIdx >> 2]); break;
-                    default: fa = magic_byte<3>(wa[byteIdx >> 2]); fb = magic_byte<3>(wb[byteIdx >> 2]); break;
+                    case 0:  fa = magic_byte<0>(wa[byteIdx >> 2], magic); fb = magic_byte<0>(wb[byteIdx >> 2], magic); break;
+                    case 1:  fa = magic_byte<1>(wa[byteIdx >> 2], magic); fb = magic_byte<1>(wb[byteIdx >> 2], magic); break;
+                    case 2:  fa = magic_byte<2>(wa[byteIdx >> 2], magic); fb = magic_byte<2>(wb[byteIdx >> 2], magic); break;
+                    default: fa = magic_byte<3>(wa[byteIdx >> 2], magic); fb = magic_byte<3>(wb[byteIdx >> 2], magic); break;
                 }
                 const u64 ab = add2(pack2(fa, fb), negMagic);          // (a - ca, b - cb), exact
                 float a, b; unpack2(ab, a, b);
                 const float d = a - b;
-                const u64 sp = pack2(d * d, a * b);                    // ((a'-b')^2, a'b')
+                const u64 sp = pack2(fmaf(d, d, k2), a * b);           // ((a'-b')^2 + k2, a'b'); k2: see the formula below
                 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int k = i - j;                                // sample i is tap k of output j
@@ -271,46 +277,50 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
                 qab1[m] = fma2(hab1, TAP(m), qab1[m + 1]);
                 qsp1[m] = fma2(hsp1, TAP(m), qsp1[m + 1]);
             }
-            qab0[10] = mul2(hab0, TAP(10)); qsp0[10] = fma2(hsp0, TAP(10), dpInit);
-            qab1[10] = mul2(hab1, TAP(10)); qsp1[10] = fma2(hsp1, TAP(10), dpInit);
+            qab0[10] = mul2(hab0, TAP(10)); qsp0[10] = mul2(hsp0, TAP(10));
+            qab1[10] = mul2(hab1, TAP(10)); qsp1[10] = mul2(hsp1, TAP(10));
 
-            const int o = blk * kBlkRows + r - 2 * kHalo;               // output row (segment-relative) completed by this input row
-            if (o >= 0 && o < nOut) {                                   // warp-uniform
-                float s[2];
-                #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float ma, mb, D, P;
-                    unpack2(c == 0 ? qab0[0] : qab1[0], ma, mb);
-                    unpack2(c == 0 ? qsp0[0] : qsp1[0], D, P);
-                    // The reference formula (src/ssim.cpp:590-704) rearranged so that numerator and denominator share
-                    // their terms:  mu_a^2 + mu_b^2 = 2 mu_a mu_b + (mu_a - mu_b)^2  and
-                    // sigma_a^2 + sigma_b^2 = 2 sigma_ab + var(a - b),  var(a-b) = E[(a'-b')^2] - (E[a'] - E[b'])^2.
-                    // Identical images then give num == den bit for bit, hence exactly 1 like the reference.
-                    // The reference's window sums to 1+eps (see gaussian_taps() in ssim_cuda.cu), which on its RAW moments
-                    // shifts every covariance by -eps*mu_a*mu_b; centred moments only see -eps*ma*mb, so the difference
-                    // -eps*(mu_a mu_b - ma mb) is applied explicitly (the matching -eps*(ca-cb)^2 of var(a-b) is already
-                    // inside D: it is the initial value of the vertical accumulators).
-                    const float mua = ma + ca, mub = mb + cb;
-                    const float t   = mua * mub;
-                    const float n1  = fmaf(2.f, t, p.c1);
-                    const float dmu = mua - mub;
-                    const float d1  = fmaf(dmu, dmu, n1);
-                    const float n2  = fmaf(-p.eps2, fmaf(-ma, mb, t), fmaf(2.f, fmaf(-ma, mb, P), p.c2));
-                    const float dm  = ma - mb;
-                    const float d2  = n2 + fmaf(-dm, dm, D);
-                    const float num = n1 * n2, den = d1 * d2;
-                    // den >= c1*c2 > 0.  MUFU.RCP + one Newton step on the quotient: ~correctly rounded, exact when num == den
-                    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
-                    const float q = num * r;
-                    s[c] = fmaf(r, fmaf(-q, den, num), q);
-                }
-                if (kMap) {
-                    float* dst = mapRow + (long long)o * p.mapPitch;
-                    if (colOk0) dst[0]  = s[0];
-                    if (colOk1) dst[32] = s[1];
-                }
-                blockSum += (colOk0 ? s[0] : 0.f) + (colOk1 ? s[1] : 0.f);
+            // Output row (segment-relative) completed by this input row.  The formula is evaluated unconditionally (rows
+            // outside [0,nOut) only cost the pipeline fill) so that its dependent chain overlaps the next row's FMAs
+            // instead of sitting behind a branch; only the store and the sum are predicated.
+            const int o = blk * kBlkRows + r - 2 * kHalo;
+            const bool rowOk = (o >= 0) && (o < nOut);
+            float s[2];
+            #pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float ma, mb, D, P;
+                unpack2(c == 0 ? qab0[0] : qab1[0], ma, mb);
+                unpack2(c == 0 ? qsp0[0] : qsp1[0], D, P);
+                // The reference formula (src/ssim.cpp:590-704) rearranged so that numerator and denominator share
+                // their terms:  mu_a^2 + mu_b^2 = 2 mu_a mu_b + (mu_a - mu_b)^2  and
+                // sigma_a^2 + sigma_b^2 = 2 sigma_ab + var(a - b),  var(a-b) = E[(a'-b')^2] - (E[a'] - E[b'])^2.
+                // Identical images then give num == den bit for bit, hence exactly 1 like the reference.
+                // The reference's window sums to 1+eps (see gaussian_taps() in ssim_cuda.cu), which on its RAW moments
+                // shifts every covariance by -eps*mu_a*mu_b; centred moments only see -eps*ma*mb, so the difference
+                // -eps*(mu_a mu_b - ma mb) is applied explicitly (the matching -eps*(ca-cb)^2 of var(a-b) is already
+                // inside D: k2 was added to every (a'-b')^2 before the blur, for free, by turning an FMUL into an FFMA).
+                const float mua = ma + ca, mub = mb + cb;
+                const float t   = mua * mub;
+                const float n1  = fmaf(2.f, t, p.c1);
+                const float dmu = mua - mub;
+                const float d1  = fmaf(dmu, dmu, n1);
+                const float n2  = fmaf(-p.eps2, fmaf(-ma, mb, t), fmaf(2.f, fmaf(-ma, mb, P), p.c2));
+                const float dm  = ma - mb;
+                const float d2  = n2 + fmaf(-dm, dm, D);
+                const float num = n1 * n2, den = d1 * d2;
+                // den >= c1*c2 > 0 on valid rows.  MUFU.RCP + one Newton step on the quotient: ~correctly rounded, exact
+                // when num == den
+                float rc; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));
+                const float q = num * rc;
+                s[c] = fmaf(rc, fmaf(-q, den, num), q);
             }
+            const bool ok0 = rowOk && colOk0, ok1 = rowOk && colOk1;
+            if (kMap) {
+                if (ok0) mapPtr[0]  = s[0];
+                if (ok1) mapPtr[32] = s[1];
+                mapPtr += p.mapPitch;
+            }
+            blockSum += (ok0 ? s[0] : 0.f) + (ok1 ? s[1] : 0.f);
         }
         total += (double)blockSum;                                      // <= 16 values per float partial
         __syncwarp();                                                   // ring is rewritten by the next horizontal pass

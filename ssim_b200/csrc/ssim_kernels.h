@@ -17,15 +17,16 @@ constexpr int kBoxW        = 128;  // TMA box width in bytes: 16 left margin + 6
 constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row: the innermost TMA coordinate (bx - 16) must be
                                    // a multiple of 16 bytes -- measured on B200: x = -16 works, x = -8 raises "illegal instruction"
                                    // (tools/dev/tma_probe.cu)
-constexpr int kStages      = 3;    // TMA ring depth per warp
+constexpr int kLoadRows    = 16;   // rows per TMA box: two blocks per load halves the (warp-wide) TMA issue overhead
+constexpr int kStages      = 2;    // TMA ring depth per warp (16-row loads)
 constexpr int kWarpsPerCta = 4;
-constexpr int kImgStageBytes = kBoxW * kBlkRows;         // 1024
-constexpr int kStageBytes    = 2 * kImgStageBytes;       // 2048 (A then B)
+constexpr int kImgStageBytes = kBoxW * kLoadRows;        // 2048
+constexpr int kStageBytes    = 2 * kImgStageBytes;       // 4096 (A then B)
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
 constexpr int kRingRowBytes   = 2 * kRingPlaneBytes;     // 1024: {E[a'], E[b']} plane then {E[(a'-b')^2], E[a'b']} plane
 constexpr int kRingBytes      = kBlkRows * kRingRowBytes; // 8192: horizontal-pass output of one block
-constexpr int kWarpSmemBytes = kStages * kStageBytes + kRingBytes;  // 14336
-constexpr int kCtaSmemBytes  = kWarpsPerCta * kWarpSmemBytes;       // 57344
+constexpr int kWarpSmemBytes = kStages * kStageBytes + kRingBytes;  // 16384
+constexpr int kCtaSmemBytes  = kWarpsPerCta * kWarpSmemBytes;       // 65536 -> 3 CTAs (12 warps) per SM
 
 struct FusedParams {
     const uint8_t* a;        // raw planes (used only to fetch the per-item centring pixel)
