@@ -290,6 +290,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];
     p.c1 = (float)((0.01 * 255) * (0.01 * 255));      // src/ssim.cpp:956-960
     p.c2 = (float)((0.03 * 255) * (0.03 * 255));
+    p.magic = 0x4B000000u;
     {
         double s1 = (double)c->taps[0];
         for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];

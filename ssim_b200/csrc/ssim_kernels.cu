@@ -150,8 +150,8 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     const float ca = (float)__ldg(p.a + (long long)frame * p.frameStrideA + (long long)cy * p.pitchA + cx);
     const float cb = (float)__ldg(p.b + (long long)frame * p.frameStrideB + (long long)cy * p.pitchB + cx);
     const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));
-    uint32_t magic;                                    // kept opaque so that it lives in a register and PRMT takes the
-    asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));   // byte selector as its immediate (no per-PRMT selector MOV)
+    const uint32_t magic = p.magic;                    // 0x4B000000, passed as a parameter so that it lives in a register and
+                                                       // PRMT takes the byte selector as its immediate (no per-PRMT selector MOV)
     const float k2     = -0.5f * p.eps2 * (ca - cb) * (ca - cb);                 // see the formula below
 
     // taps: w[m] multiplies the sample at offset m of an 11-sample window, w[m] = g[|m-5|]
@@ -389,21 +389,17 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ dA, long long pitchA, ui
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static cudaError_t ensure_smem_attr()
+// cudaFuncSetAttribute is per DEVICE: called from every device context's initialisation (current device = that device)
+static cudaError_t set_smem_attr()
 {
-    static cudaError_t status = [] {
-        cudaError_t e = cudaFuncSetAttribute(ssim_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(ssim_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
-    }();
-    return status;
+    cudaError_t e = cudaFuncSetAttribute(ssim_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ssim_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
 }
 
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA8, const CUtensorMap& tmA1,
                          const CUtensorMap& tmB8, const CUtensorMap& tmB1, const FusedParams& p)
 {
-    cudaError_t e = ensure_smem_attr();
-    if (e != cudaSuccess) return e;
     const long long ctas = (p.items + kWarpsPerCta - 1) / kWarpsPerCta;
     if (ctas <= 0 || ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     if (p.map) ssim_fused_kernel<true><<<(unsigned)ctas, kWarpsPerCta * 32, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
@@ -419,7 +415,7 @@ cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int fr
 
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm)
 {
-    cudaError_t e = ensure_smem_attr();
+    cudaError_t e = set_smem_attr();
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
     if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<true>)) != cudaSuccess) return e;

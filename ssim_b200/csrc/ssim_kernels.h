@@ -40,6 +40,7 @@ struct FusedParams {
     long long items;
     float g[6];              // separable 11-tap weights: g[d] is the tap at distance d from the centre
     float c1, c2;
+    uint32_t magic;          // 0x4B000000 (float 2^23): kept opaque to ptxas, see the kernel
     float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
 };
 
@@ -54,6 +55,7 @@ struct FinalizeParams {
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA8, const CUtensorMap& tmA1,
                          const CUtensorMap& tmB8, const CUtensorMap& tmB1, const FusedParams& p);
 cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames);
+// per-device preparation (sets the dynamic shared-memory limit on the CURRENT device) + kernel facts
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm);
 
 // layout helpers

@@ -1,0 +1,118 @@
+"""GPU tests of the device-resident entry points (frames, strips, multi-GPU) against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GLOBAL_TOL, PIXEL_TOL
+from ssim_b200 import api, parallel
+from ssim_b200.synth import synth_pair
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev(x):
+    return torch.from_numpy(x).cuda()
+
+
+def test_batch_of_frames_matches_per_frame_oracle():
+    """BASELINE.json configs[4] in miniature: N frame pairs, one launch, per-frame SSIM + maps"""
+    F, W, H = 5, 208, 77                       # pitch 208 is a multiple of 16
+    a = np.stack([synth_pair(W, H, f)[0] for f in range(F)])
+    b = np.stack([synth_pair(W, H, f)[1] for f in range(F)])
+    dA, dB = _dev(a), _dev(b)
+    dMap = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+    dSums = torch.empty(F, dtype=torch.float64, device="cuda")
+    dSsim = torch.empty(F, dtype=torch.float32, device="cuda")
+    api.compute_device(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, F, dA.data_ptr(), W, W * H, dB.data_ptr(), W, W * H,
+                       dMap.data_ptr(), W, W * H, dSums.data_ptr(), dSsim.data_ptr())
+    torch.cuda.synchronize()
+    assert api.cuda_lib().ssim_cuda_last_launch_count() == 2
+    for f in range(F):
+        o, tot, om = oracle.oracle_ssim(a[f], b[f], want_map=True)
+        assert abs(float(dSsim[f]) - float(o)) <= GLOBAL_TOL
+        assert abs(float(dSums[f]) - tot) <= 1e-6 * W * H
+        assert np.abs(dMap[f].cpu().numpy() - om).max() <= PIXEL_TOL
+    # synth_fill on the device produces the same bytes as the host recipe
+    dA2, dB2 = torch.empty_like(dA[0]), torch.empty_like(dB[0])
+    api.synth_fill(0, torch.cuda.current_stream().cuda_stream, dA2.data_ptr(), W, dB2.data_ptr(), W, W, H, 0, 3)
+    assert np.array_equal(dA2.cpu().numpy(), a[3]) and np.array_equal(dB2.cpu().numpy(), b[3])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_strips_with_halo_rows_reproduce_the_full_image(world):
+    """BASELINE.json configs[3] in miniature: strips + 5 halo rows; sum of partial sums == full-image sum.
+    All 'ranks' run on GPU 0 here; tests/test_host_logic.py covers the 2-process reduction with gloo."""
+    W, H = 336, 203
+    a, b = synth_pair(W, H, 6)
+    o, tot, om = oracle.oracle_ssim(a, b, want_map=True)
+    got_map = np.zeros((H, W), np.float32)
+    total = 0.0
+    for r in range(world):
+        s0, s1, oy, orows = parallel.strip_bounds(H, world, r)
+        dA, dB = _dev(np.ascontiguousarray(a[s0:s1])), _dev(np.ascontiguousarray(b[s0:s1]))
+        dMap = torch.empty((orows, W), dtype=torch.float32, device="cuda")
+        dSum = torch.empty(1, dtype=torch.float64, device="cuda")
+        api.compute_device(0, None, W, s1 - s0, oy, orows, 1, dA.data_ptr(), W, 0, dB.data_ptr(), W, 0, dMap.data_ptr(), W, 0,
+                           dSum.data_ptr(), None)
+        torch.cuda.synchronize()
+        got_map[s0 + oy:s0 + oy + orows] = dMap.cpu().numpy()
+        total += float(dSum.item())
+    assert abs(float(parallel.mean_from_partials(total, W, H)) - float(o)) <= GLOBAL_TOL
+    assert np.abs(got_map - om).max() <= PIXEL_TOL
+
+
+def test_compute_strips_entry_point():
+    """ssim_cuda_compute_strips(): host image split across the GPUs of this process (+ NCCL when there are >= 2)"""
+    n = api.cuda_lib().ssim_cuda_device_count()
+    a, b = synth_pair(500, 333, 8)
+    o, _, om = oracle.oracle_ssim(a, b, want_map=True)
+    for devices in ([0], list(range(min(n, 2))), list(range(n))):
+        s, m = api.compute_strips(devices, a, b, want_map=True)
+        assert abs(float(s) - float(o)) <= GLOBAL_TOL, devices
+        assert np.abs(m - om).max() <= PIXEL_TOL
+    out = C.c_float()
+    devs = (C.c_int * 2)(0, 0)
+    assert api.cuda_lib().ssim_cuda_compute_strips(2, devs, 500, 333, a.ctypes.data, 1, 500, b.ctypes.data, 1, 500, None, 0, 0, C.byref(out)) == 22
+
+
+def test_device_pointers_through_the_reference_api():
+    """rmgr_ssim_compute_ssim() accepts device pointers for images and map (detected per pointer)"""
+    W, H = 320, 90
+    a, b = synth_pair(W, H, 2)
+    o, _, om = oracle.oracle_ssim(a, b, want_map=True)
+    dA, dB = _dev(a), _dev(b)
+    dMap = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+    p = api.Params()
+    p.width, p.height = W, H
+    p.imgA.topLeft, p.imgA.step, p.imgA.stride = dA.data_ptr(), 1, W
+    p.imgB.topLeft, p.imgB.step, p.imgB.stride = dB.data_ptr(), 1, W
+    p.ssimMap, p.ssimStep, p.ssimStride = dMap.data_ptr(), 1, W
+    out = C.c_float()
+    assert api.rmgr_lib().rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 0
+    assert abs(out.value - float(o)) <= GLOBAL_TOL and np.abs(dMap.cpu().numpy() - om).max() <= PIXEL_TOL
+    # interleaved device image (step 3) + misaligned base goes through the pack kernel
+    rgb = np.zeros((H, W, 3), np.uint8)
+    rgb[..., 1] = a
+    rgb2 = np.zeros((H, W, 3), np.uint8)
+    rgb2[..., 1] = b
+    dR, dR2 = _dev(rgb), _dev(rgb2)
+    p.imgA.topLeft, p.imgA.step, p.imgA.stride = dR.data_ptr() + 1, 3, 3 * W
+    p.imgB.topLeft, p.imgB.step, p.imgB.stride = dR2.data_ptr() + 1, 3, 3 * W
+    p.ssimMap = None
+    assert api.rmgr_lib().rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 0
+    assert abs(out.value - float(o)) <= GLOBAL_TOL
+
+
+def test_device_argument_errors():
+    lib = api.cuda_lib()
+    t = torch.zeros(64 * 64, dtype=torch.uint8, device="cuda")
+    s = torch.zeros(1, dtype=torch.float64, device="cuda")
+    f = lib.ssim_cuda_compute_device
+    assert f(0, None, 64, 64, 0, 64, 1, t.data_ptr(), 64, 0, t.data_ptr(), 64, 0, None, 0, 0, None, None) == 22      # no output
+    assert f(0, None, 64, 64, 0, 65, 1, t.data_ptr(), 64, 0, t.data_ptr(), 64, 0, None, 0, 0, s.data_ptr(), None) == 22  # rows out of range
+    assert f(0, None, 60, 64, 0, 64, 1, t.data_ptr(), 60, 0, t.data_ptr(), 60, 0, None, 0, 0, s.data_ptr(), None) == 22  # pitch % 16
+    assert f(0, None, 64, 64, 0, 64, 1, t.data_ptr() + 4, 64, 0, t.data_ptr(), 64, 0, None, 0, 0, s.data_ptr(), None) == 22  # base % 16
+    assert f(99, None, 64, 64, 0, 64, 1, t.data_ptr(), 64, 0, t.data_ptr(), 64, 0, None, 0, 0, s.data_ptr(), None) == 22  # bad device

@@ -1,0 +1,162 @@
+"""CPU-only tests of the host side: ABI layouts, exported symbols, pure-host API helpers, sharding logic
+(world_size-2 gloo).  No compute call is made here: there is no GPU in the build container and no CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from ssim_b200 import _abi, api, parallel
+from ssim_b200.synth import synth_pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols(header, prefix):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s\w+)\s*\(" % prefix, text)))
+
+
+def test_struct_layouts_match_reference_abi():
+    """24 / 96 / 24 bytes on LP64, field offsets as in the reference's ssim.h:489-533"""
+    assert C.sizeof(_abi.ImgParams) == 24 and C.sizeof(_abi.Params) == 96 and C.sizeof(_abi.ThreadPool) == 24
+    assert _abi.Params.imgA.offset == 8 and _abi.Params.imgB.offset == 32 and _abi.Params.ssimMap.offset == 56
+    assert _abi.Params.ssimStep.offset == 64 and _abi.Params.ssimStride.offset == 72 and _abi.Params.alloc.offset == 80
+
+
+def test_libssim_cuda_exports_every_declared_symbol():
+    lib = api.cuda_lib()
+    names = _declared_symbols("ssim_cuda.h", "ssim_cuda_")
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.ssim_cuda_abi_version() == 1
+    assert lib.ssim_cuda_last_error_string() is not None
+
+
+def test_librmgr_exports_reference_api():
+    lib = api.rmgr_lib()
+    for n in _declared_symbols("rmgr/ssim.h", "rmgr_ssim_") + _declared_symbols("rmgr/ssim-openmp.h", "rmgr_ssim_"):
+        if n.endswith("Fct"):
+            continue
+        assert hasattr(lib, n), n
+    # the two C++ overloads (mangled exactly as a caller compiled against the reference's header expects)
+    out = subprocess.run(["nm", "-D", os.path.join(api.LIB_DIR, "librmgr-ssim.so")], capture_output=True, text=True).stdout
+    assert "_ZN4rmgr4ssim12compute_ssimEPfRK17rmgr_ssim_Params_PK21rmgr_ssim_ThreadPool_" in out
+    assert "_ZN4rmgr4ssim12compute_ssimERKNS0_6ParamsE" in out
+
+
+def test_pure_host_api_helpers():
+    """get_version / init_interleaved / init_planar / use_default_allocator: reference src/ssim.cpp:156-217,1126-1142"""
+    lib = api.rmgr_lib()
+    assert api.get_version() == (2, 1, 0, "2.1.0")
+    assert lib.rmgr_ssim_get_version(None) == 22
+    buf = np.zeros(64, np.uint8)
+    ip = _abi.ImgParams()
+    assert lib.rmgr_ssim_init_interleaved(C.byref(ip), buf.ctypes.data, -24, 3, 2) == 0
+    assert (ip.topLeft, ip.step, ip.stride) == (buf.ctypes.data + 2, 3, -24)
+    assert lib.rmgr_ssim_init_interleaved(C.byref(ip), buf.ctypes.data, 24, 3, 3) == 22       # channelNum >= channelCount
+    assert lib.rmgr_ssim_init_interleaved(None, buf.ctypes.data, 24, 3, 0) == 22
+    assert lib.rmgr_ssim_init_interleaved(C.byref(ip), None, 24, 3, 0) == 22
+    planes = (C.c_void_p * 2)(buf.ctypes.data, buf.ctypes.data + 32)
+    strides = (C.c_ssize_t * 2)(8, 16)
+    assert lib.rmgr_ssim_init_planar(C.byref(ip), planes, strides, 1) == 0
+    assert (ip.topLeft, ip.step, ip.stride) == (buf.ctypes.data + 32, 1, 16)
+    assert lib.rmgr_ssim_init_planar(C.byref(ip), None, strides, 0) == 22
+    p = _abi.Params()
+    assert lib.rmgr_ssim_use_default_allocator(C.byref(p)) == 0 and p.alloc and p.dealloc
+    assert lib.rmgr_ssim_use_default_allocator(None) == 22
+
+
+def test_validation_happens_before_any_device_work():
+    """EINVAL paths of compute_ssim (reference src/ssim.cpp:962-978) return without touching CUDA"""
+    lib = api.rmgr_lib()
+    a = np.zeros((4, 4), np.uint8)
+    out = C.c_float()
+    p = _abi.make_params(a, a, 4, 4)
+    assert lib.rmgr_ssim_compute_ssim(None, C.byref(p), None) == 22
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), None, None) == 22
+    p.imgB.topLeft = None
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 22
+    p = _abi.make_params(a, a, 4, 0)
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 22
+
+
+def test_no_cpu_fallback_without_a_device():
+    lib = api.cuda_lib()
+    if lib.ssim_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    a = np.zeros((8, 8), np.uint8)
+    with pytest.raises(api.SsimError) as e:
+        api.compute_ssim(a, a)
+    assert e.value.errno == 19                                                              # ENODEV, never a silent CPU result
+
+
+def test_strip_bounds_cover_the_image():
+    for h, n in [(16384, 8), (2160, 4), (7, 8), (1080, 3), (11, 2)]:
+        rows = 0
+        for g in range(n):
+            s0, s1, oy, orows = parallel.strip_bounds(h, n, g)
+            assert 0 <= s0 <= s1 <= h and s0 + oy + orows <= s1
+            assert (s0 + oy) == h * g // n
+            # interior edges carry the full halo, exterior edges none
+            assert oy == min(5, h * g // n) and s1 - (s0 + oy + orows) == min(5, h - h * (g + 1) // n)
+            rows += orows
+        assert rows == h
+    assert [parallel.shard_frames(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import oracle
+from ssim_b200 import parallel
+from ssim_b200.synth import synth_pair
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+W, H = 150, 61
+# --- one image in strips with halos: each rank only ever touches ITS rows; partial sums all-reduced (SUM of doubles)
+s0, s1, oy, orows = parallel.strip_bounds(H, world, rank)
+a, b = synth_pair(W, s1 - s0, 4, y0=s0)
+_, _, m = oracle.oracle_ssim(a, b, want_map=True)            # clamps at the strip's own edges
+part = torch.tensor([float(m[oy:oy + orows].astype(np.float64).sum())], dtype=torch.float64)
+dist.all_reduce(part, op=dist.ReduceOp.SUM)
+fa, fb = synth_pair(W, H, 4)
+full, tot, fm = oracle.oracle_ssim(fa, fb, want_map=True)
+assert abs(part.item() - fm.astype(np.float64).sum()) < 1e-9, (part.item(), tot)
+assert parallel.mean_from_partials(part.item(), W, H) == np.float32(fm.astype(np.float64).sum() / (W * H))
+assert np.abs(m[oy:oy + orows] - fm[s0 + oy:s0 + oy + orows]).max() == 0.0     # halo rows make strips exact
+# --- a frame batch sharded across ranks, results gathered
+f0, f1 = parallel.shard_frames(5, world, rank)
+mine = torch.zeros(5, dtype=torch.float64)
+for f in range(f0, f1):
+    x, y = synth_pair(40, 30, f)
+    mine[f] = float(oracle.oracle_ssim(x, y)[0])
+dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+want = [float(oracle.oracle_ssim(*synth_pair(40, 30, f))[0]) for f in range(5)]
+assert np.allclose(mine.numpy(), want, atol=0), (mine, want)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_strips_and_batch(tmp_path):
+    """N>1 host logic on CPU: world_size 2, gloo backend, rendezvous on 127.0.0.1"""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    procs = [subprocess.Popen([sys.executable, str(script), str(port), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
