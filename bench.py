@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE.json configs (1080p, 16384^2 strips, 1080p batch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     return ap.parse_args()
 
@@ -169,6 +170,79 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ secondary configs
+def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
+    """BASELINE.json configs[1], [3], [4], measured the same way (device-timed, max over ranks); informational."""
+    from ssim_b200 import parallel
+    dev = torch.device("cuda", local)
+    sh = stream.cuda_stream
+    out = {}
+
+    def timed(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # configs[1]: one 1920x1080 pair, global SSIM only (no map)
+    w, h = 1920, 1080
+    a = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    b = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    sums = torch.empty(1, dtype=torch.float64, device=dev)
+    val = torch.empty(1, dtype=torch.float32, device=dev)
+    api.synth_fill(local, sh, a.data_ptr(), w, b.data_ptr(), w, w, h, 0, 0)
+    ms = timed(lambda: api.compute_device(local, sh, w, h, 0, h, 1, a.data_ptr(), w, 0, b.data_ptr(), w, 0, None, 0, 0, sums.data_ptr(), val.data_ptr()), 20)
+    out["1080p_pair_no_map"] = {"us_per_pair": round(ms * 1e3, 2), "mpix_per_s": round(w * h / ms / 1e3, 1), "ssim": float(val.item()),
+                                "note": "one pair per launch on every rank (latency view, L2-resident)"}
+
+    # configs[3]: ONE 16384x16384 pair split into row strips with 5-row halos across the ranks, map strips written,
+    # double partial sums all-reduced with NCCL inside the timed region
+    W16 = 16384
+    s0, s1, oy, orows = parallel.strip_bounds(W16, world, rank)
+    a = torch.empty((s1 - s0, W16), dtype=torch.uint8, device=dev)
+    b = torch.empty((s1 - s0, W16), dtype=torch.uint8, device=dev)
+    m = torch.empty((orows, W16), dtype=torch.float32, device=dev)
+    api.synth_fill(local, sh, a.data_ptr(), W16, b.data_ptr(), W16, W16, s1 - s0, s0, 0)
+
+    def strips():
+        api.compute_device(local, sh, W16, s1 - s0, oy, orows, 1, a.data_ptr(), W16, 0, b.data_ptr(), W16, 0, m.data_ptr(), W16, 0, sums.data_ptr(), None)
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+
+    ms = timed(strips, 10)
+    strips()
+    torch.cuda.synchronize()
+    out["16384x16384_strips_with_map"] = {"ms": round(ms, 4), "mpix_per_s": round(W16 * W16 / ms / 1e3, 1), "scaling": "strong",
+                                          "ssim": float(parallel.mean_from_partials(float(sums.item()), W16, W16)),
+                                          "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce of 1 double per step"}
+    del a, b, m
+
+    # configs[4]: 4096 x 1080p pairs with maps, 512 per GPU (weak scaling; fewer per GPU when more than 8 ranks are not available)
+    F = 512
+    w, h = 1920, 1080
+    a = torch.empty((F, h, w), dtype=torch.uint8, device=dev)
+    b = torch.empty((F, h, w), dtype=torch.uint8, device=dev)
+    m = torch.empty((F, h, w), dtype=torch.float32, device=dev)
+    fs = torch.empty(F, dtype=torch.float64, device=dev)
+    fv = torch.empty(F, dtype=torch.float32, device=dev)
+    for f in range(F):
+        api.synth_fill(local, sh, a[f].data_ptr(), w, b[f].data_ptr(), w, w, h, 0, rank * F + f)
+    ms = timed(lambda: api.compute_device(local, sh, w, h, 0, h, F, a.data_ptr(), w, w * h, b.data_ptr(), w, w * h, m.data_ptr(), w, w * h,
+                                          fs.data_ptr(), fv.data_ptr()), 5)
+    out["1080p_batch_512_per_gpu_with_maps"] = {"ms": round(ms, 3), "mpix_per_s": round(world * F * w * h / ms / 1e3, 1), "scaling": "weak",
+                                                "ssim_first_last": [float(fv[0].item()), float(fv[-1].item())]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -292,6 +366,8 @@ def run_ours(args):
         dist.all_reduce(td, op=dist.ReduceOp.MAX)
     e2e_value = n * F * npx * e2e_steps / float(td.item()) / 1e6
 
+    extras = None if args.no_extras else run_extras(args, api, torch, dist, local, rank, world, stream, barrier)
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -328,6 +404,8 @@ def run_ours(args):
             "single_pair_us": {"median": round(statistics.median(single), 2), "min": round(min(single), 2),
                                "mpix_per_s_at_median": round(npx / statistics.median(single), 1)},
             "ssim_frame0": ssim_first, "ssim_e2e_last": float(e2e_last)}
+    if extras is not None:
+        line["other_configs"] = extras
 
     if n == 1 and not args.no_cpu_baseline:
         import oracle

@@ -167,7 +167,12 @@ struct Context {
     int device = -1;
     int numSMs = 0;
     int ctasPerSm = 3;
-    cudaStream_t stream = nullptr;            // stream of the blocking host-pointer path
+    cudaStream_t stream = nullptr;            // stream of the blocking host-pointer path (compute)
+    cudaStream_t streamIn = nullptr;          // pipelined host path: H2D copies
+    cudaStream_t streamOut = nullptr;         // pipelined host path: D2H copies
+    static const int kMaxChunks = 32;
+    cudaEvent_t evIn[kMaxChunks] = {}, evDone[kMaxChunks] = {};
+    Buffer chunkSums, chunkSumsHost;          // one double per chunk (device, pinned host)
     std::mutex hostPathMutex;                 // the host path shares the scratch below
     Buffer planeA, planeB, rawA, rawB, map, stage;
     Buffer scalars;                           // double sum + float ssim of the host path
@@ -198,6 +203,13 @@ int get_context(int device, Context** out)
     c->stage.pinnedHost = true;
     gaussian_taps(c->taps);
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->streamIn, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->streamOut, cudaStreamNonBlocking));
+    for (int i = 0; i < Context::kMaxChunks; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->evDone[i], cudaEventDisableTiming));
+    }
+    c->chunkSumsHost.pinnedHost = true;
     int regsMap = 0, regsNoMap = 0, ctas = 0;
     CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &ctas));
     c->ctasPerSm = std::max(1, ctas);
@@ -213,18 +225,18 @@ int get_context(int device, Context** out)
 void choose_segments(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, int* segRows, int* segs)
 {
     const long long bands = (width + ssimk::kBandW - 1) / ssimk::kBandW;
-    const long long slots = (long long)c->numSMs * c->ctasPerSm * ssimk::kWarpsPerCta;   // resident warps
+    const long long slots = (long long)c->numSMs * c->ctasPerSm * ssimk::kPairsPerCta;   // resident work items (one producer + one consumer warp each)
     const long long units = bands * frames;
     long long s;
+    const long long tall = std::max<long long>(1, outRows / 256);      // segments per frame if they stay >= 256 rows (halo <= 4%)
     if (g_segRowsOverride > 0) {
         s = (outRows + g_segRowsOverride - 1) / g_segRowsOverride;
-    } else if (units * ((outRows + 63) / 64) <= slots) {
-        s = (outRows + 63) / 64;                       // tiny problem: segments of >= 64 rows, less than one wave
-    } else if (units >= slots) {
-        // several waves anyway: aim for >= 8 waves of items, keep segments >= 128 rows
-        s = std::max<long long>(1, std::min<long long>((8 * slots + units - 1) / units, outRows / 128));
+    } else if (units * tall >= 4 * slots) {
+        // plenty of work: several waves of tall segments (dynamic CTA scheduling evens out the tail)
+        s = std::min<long long>(tall, (8 * slots + units - 1) / units);
     } else {
-        s = std::max<long long>(1, slots / units);     // exactly one wave, as full as possible
+        // latency regime (one image / a few frames): exactly one wave, as full as possible
+        s = std::max<long long>(1, slots / units);
     }
     s = std::max<long long>(1, std::min<long long>(s, outRows));
     int rows = (int)((outRows + s - 1) / s);
@@ -449,10 +461,73 @@ int finish_general(const GeneralJob& job)
     return 0;
 }
 
+// Large host images in plain row layout: the image is cut into row chunks and three streams overlap the H2D copy of
+// chunk k+1, the kernel of chunk k and the map D2H of chunk k-1 (PCIe is full duplex; the kernel is ~10x faster than
+// either copy, so a blocking call costs about max(H2D, D2H) instead of H2D + kernel + D2H).  A chunk's kernel reads rows
+// up to 5 below its last output row, so its H2D covers 5 extra rows; everything lands in one full-height device plane and
+// the kernel addresses it with (srcRows = H, outY0, outRows), i.e. exactly the strip mechanism of the multi-GPU path.
+int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t strideA, const uint8_t* b, ptrdiff_t strideB,
+                      float* map, ptrdiff_t mapStride, float* ssim)
+{
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t pitch = align_up(W, 16), mapPitch = align_up(W, 4);
+    int rc;
+    if ((rc = c->planeA.ensure(pitch * H)) || (rc = c->planeB.ensure(pitch * H))) return rc;
+    if (map && (rc = c->map.ensure(mapPitch * H * sizeof(float)))) return rc;
+    const uint32_t targetRows = std::max<uint32_t>(64, (uint32_t)((1u << 20) / std::max<uint32_t>(W, 1)));   // ~1 MB of pixels per chunk and image
+    int nChunks = (int)std::min<uint32_t>(Context::kMaxChunks, (H + targetRows - 1) / targetRows);
+    nChunks = std::max(nChunks, 2);
+    if ((rc = c->chunkSums.ensure(sizeof(double) * Context::kMaxChunks)) || (rc = c->chunkSumsHost.ensure(sizeof(double) * Context::kMaxChunks))) return rc;
+    uint8_t *dA = (uint8_t*)c->planeA.ptr, *dB = (uint8_t*)c->planeB.ptr;
+    float* dMap = map ? (float*)c->map.ptr : nullptr;
+    double* dSums = (double*)c->chunkSums.ptr;
+
+    uint32_t copied = 0;                                       // rows [0, copied) are on the device (or in flight on streamIn)
+    for (int k = 0; k < nChunks; ++k) {
+        const uint32_t y0 = (uint32_t)((uint64_t)H * k / nChunks), y1 = (uint32_t)((uint64_t)H * (k + 1) / nChunks);
+        const uint32_t need = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
+        if (need > copied) {
+            CU_TRY(cudaMemcpy2DAsync(dA + (size_t)copied * pitch, pitch, a + (ptrdiff_t)copied * strideA, (size_t)strideA, W, need - copied,
+                                     cudaMemcpyHostToDevice, c->streamIn));
+            CU_TRY(cudaMemcpy2DAsync(dB + (size_t)copied * pitch, pitch, b + (ptrdiff_t)copied * strideB, (size_t)strideB, W, need - copied,
+                                     cudaMemcpyHostToDevice, c->streamIn));
+            copied = need;
+        }
+        CU_TRY(cudaEventRecord(c->evIn[k], c->streamIn));
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->evIn[k], 0));
+        if (y1 == y0) { CU_TRY(cudaMemsetAsync(dSums + k, 0, sizeof(double), c->stream)); continue; }
+        rc = compute_device_impl(c, c->stream, W, H, y0, y1 - y0, 1, dA, pitch, 0, dB, pitch, 0,
+                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, dSums + k, nullptr);
+        if (rc) return rc;
+        if (map) {
+            CU_TRY(cudaEventRecord(c->evDone[k], c->stream));
+            CU_TRY(cudaStreamWaitEvent(c->streamOut, c->evDone[k], 0));
+            CU_TRY(cudaMemcpy2DAsync(map + (ptrdiff_t)y0 * mapStride, (size_t)mapStride * sizeof(float), dMap + (size_t)y0 * mapPitch,
+                                     mapPitch * sizeof(float), (size_t)W * sizeof(float), y1 - y0, cudaMemcpyDeviceToHost, c->streamOut));
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(c->chunkSumsHost.ptr, dSums, sizeof(double) * nChunks, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (map) CU_TRY(cudaStreamSynchronize(c->streamOut));
+    if (ssim) {
+        double total = 0.0;                                    // fixed order: deterministic
+        for (int k = 0; k < nChunks; ++k) total += ((const double*)c->chunkSumsHost.ptr)[k];
+        *ssim = (float)(total / (double)(uint32_t)(W * H));    // src/ssim.cpp:1102
+    }
+    return 0;
+}
+
 int compute_general(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA, const uint8_t* b,
                     ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
 {
     std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    // pipelined path: plain-row host images (and host map) large enough for the overlap to pay.  Pageable memory works
+    // too (the runtime stages it), pinned memory gets the full overlap.
+    if ((uint64_t)W * H >= (1u << 21) && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
+        classify(a) == Where::Host && classify(b) == Where::Host &&
+        (map == nullptr || (mapStep == 1 && mapStride >= (ptrdiff_t)W && classify(map) == Where::Host)) &&
+        getenv("SSIM_CUDA_NO_PIPELINE") == nullptr)
+        return compute_pipelined(c, W, H, a, strideA, b, strideB, map, mapStride, ssim);
     GeneralJob job;
     int rc = enqueue_general(c, W, H, 0, H, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job);
     if (rc) return rc;
@@ -599,7 +674,10 @@ void ssim_cuda_shutdown(void)
         Context* c = kv.second;
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
-        for (Buffer* b : {&c->planeA, &c->planeB, &c->rawA, &c->rawB, &c->map, &c->stage, &c->scalars}) b->release();
+        for (Buffer* b : {&c->planeA, &c->planeB, &c->rawA, &c->rawB, &c->map, &c->stage, &c->scalars, &c->chunkSums, &c->chunkSumsHost}) b->release();
+        for (int i = 0; i < Context::kMaxChunks; ++i) { if (c->evIn[i]) cudaEventDestroy(c->evIn[i]); if (c->evDone[i]) cudaEventDestroy(c->evDone[i]); }
+        if (c->streamIn) cudaStreamDestroy(c->streamIn);
+        if (c->streamOut) cudaStreamDestroy(c->streamOut);
         for (auto& p : c->partials) p.second.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         delete c;

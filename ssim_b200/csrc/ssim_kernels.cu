@@ -77,220 +77,283 @@ template <int kByte>
 __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t magic) { return __uint_as_float(__byte_perm(word, magic, 0x7440 + kByte)); }
 
 // ------------------------------------------------------------------------------------------------ fused kernel
-template <bool kMap>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
-ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmB8, const __grid_constant__ CUtensorMap tmB1,
-                  const __grid_constant__ FusedParams p)
+// Work item = (frame, row segment, 64-column band).  Each item is served by a PAIR of warps of the same CTA:
+//
+//   producer warp (warps 0-3)   TMA loads of 8-row u8 boxes into a 3-stage ring, clamp patching, u8 -> f32, products,
+//                               horizontal 11-tap pass; writes 8-row blocks of {E_h[a'], E_h[b']}, {E_h[(a'-b')^2], E_h[a'b']}
+//                               into a 22-row shared-memory ring = two halves of 11 rows (full/empty mbarrier per half)
+//   consumer warp (warps 4-7)   vertical 11-tap pass with eleven IN-PLACE accumulators per plane pair: its loop body is
+//                               exactly half the ring = 11 rows, fully unrolled, so accumulator slot s always owns the
+//                               output rows == s (mod 11), every tap index is static and nothing has to be shifted or
+//                               renamed across iterations; then the SSIM formula, map store and partial sums
+//
+// The two roles overlap in time (the consumer's dependent formula chain hides behind the producer's FMAs and vice versa),
+// setmaxnreg moves registers from the producers (96) to the consumers (160), and nothing is ever synchronised CTA-wide
+// after the prologue.
+struct ItemCoords {
+    int frame, bx, oy0, nOut, inY0;
+    int nBodies;    // 11-row bodies the consumer runs: ceil((nOut + 10) / 11)
+    int nBlk;       // 8-row blocks the producer makes: ceil(11 * nBodies / 8) (rows past the segment are clamp-loaded filler)
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+// try_wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots in a spin loop
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity), "r"(2000u) : "memory");
+}
+
+// (frame, segment, band) of a work item, band fastest so that a CTA covers 4 adjacent bands; plus the per-item centring
+// pixels: moments are accumulated on (a - ca), (b - cb), which keeps the fp32 cancellation in E[x^2] - mu^2 small even on
+// flat regions (DESIGN.md "Numerics").  Any integer works; both warps of a pair must of course use the same one.
+__device__ __forceinline__ void decode_item(const FusedParams& p, long long item, ItemCoords& it, float& ca, float& cb)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kStages];
+    const int band = (int)(item % p.bands);
+    const int seg  = (int)((item / p.bands) % p.segs);
+    it.frame = (int)(item / ((long long)p.bands * p.segs));
+    it.bx    = band * kBandW;                                           // first output column of the band
+    it.oy0   = p.outY0 + seg * p.segRows;                               // first output row (plane coordinates)
+    it.nOut  = min(p.segRows, p.outY0 + p.outRows - it.oy0);            // output rows of this item
+    it.inY0  = it.oy0 - kHalo;                                          // first input row needed (may be negative)
+    it.nBodies = (it.nOut + 2 * kHalo + kTaps - 1) / kTaps;
+    it.nBlk    = (it.nBodies * kTaps + kBlkRows - 1) / kBlkRows;
+    const int cx = min(it.bx + kBandW / 2, p.width - 1);
+    const int cy = min(max(it.oy0, 0), p.srcRows - 1);
+    ca = (float)__ldg(p.a + (long long)it.frame * p.frameStrideA + (long long)cy * p.pitchA + cx);
+    cb = (float)__ldg(p.b + (long long)it.frame * p.frameStrideB + (long long)cy * p.pitchB + cx);
+}
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (item >= p.items) return;                       // warps are independent: no CTA-wide barrier anywhere below
+// ---- producer: TMA + horizontal pass
+__device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUtensorMap* tmA1, const CUtensorMap* tmB8,
+                                              const CUtensorMap* tmB1, const FusedParams& p, const ItemCoords& it, int lane,
+                                              uint32_t pairSmem, uint32_t barTma, uint32_t barFull, uint32_t barEmpty, float ca, float cb)
+{
+    const uint32_t ringBase = pairSmem + kStages * kStageBytes;
 
-    // ---- decode the work item: (frame, segment, band), band fastest so that a CTA covers 4 adjacent bands
-    const int band  = (int)(item % p.bands);
-    const int seg   = (int)((item / p.bands) % p.segs);
-    const int frame = (int)(item / ((long long)p.bands * p.segs));
-    const int bx    = band * kBandW;                                 // first output column of the band
-    const int oy0   = p.outY0 + seg * p.segRows;                     // first output row (plane coordinates)
-    const int nOut  = min(p.segRows, p.outY0 + p.outRows - oy0);     // output rows of this item
-    const int inY0  = oy0 - kHalo;                                   // first input row needed (may be negative)
-    const int nBlk  = (nOut + 2 * kHalo + kBlkRows - 1) / kBlkRows;
-
-    const uint32_t warpSmem = smem_u32(smem) + warp * kWarpSmemBytes;
-    const uint32_t ringBase = warpSmem + kStages * kStageBytes;
-    const uint32_t barBase  = smem_u32(&bars[warp][0]);
-
-    if (lane == 0) {
-        #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(barBase + 8 * s, 1);
-        fence_mbar_init();
-        fence_proxy_async();
-    }
-    __syncwarp();
-
-    // One TMA load = rows [inY0 + 16*ld, +16) x bytes [bx-16, bx+112) of both images = two 8-row blocks.  Rows outside
-    // the plane are clamped by loading single-row boxes at clamped coordinates (replicates the nearest row,
-    // src/ssim.cpp:562-582); columns outside the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
-    const int nLoads = (nBlk + 1) >> 1;
-    auto issue_load = [&](int ld) {
-        const int stage = ld & (kStages - 1);
-        const uint32_t bar = barBase + 8 * stage;
-        const uint32_t dst = warpSmem + stage * kStageBytes;
-        const int y = inY0 + ld * kLoadRows;
+    // One TMA load = rows [inY0 + 8*blk, +8) x bytes [bx-16, bx+112) of both images.  Rows outside the plane are clamped by
+    // loading single-row boxes at clamped coordinates (replicates the nearest row, src/ssim.cpp:562-582); columns outside
+    // the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
+    auto issue_load = [&](int blk) {
         if (lane == 0) {
             // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes)
+            const int stage = blk % kStages;
+            const uint32_t bar = barTma + 8 * stage;
+            const uint32_t dst = pairSmem + stage * kStageBytes;
+            const int y = it.inY0 + blk * kLoadRows;
             mbar_arrive_expect_tx(bar, kStageBytes);
             if (y >= 0 && y + kLoadRows <= p.srcRows) {
-                tma_load_3d(dst, &tmA8, bx - kBoxLeft, y, frame, bar);
-                tma_load_3d(dst + kImgStageBytes, &tmB8, bx - kBoxLeft, y, frame, bar);
+                tma_load_3d(dst, tmA8, it.bx - kBoxLeft, y, it.frame, bar);
+                tma_load_3d(dst + kImgStageBytes, tmB8, it.bx - kBoxLeft, y, it.frame, bar);
             } else {
                 #pragma unroll 1
                 for (int r = 0; r < kLoadRows; ++r) {
                     const int yy = min(max(y + r, 0), p.srcRows - 1);
-                    tma_load_3d(dst + r * kBoxW, &tmA1, bx - kBoxLeft, yy, frame, bar);
-                    tma_load_3d(dst + kImgStageBytes + r * kBoxW, &tmB1, bx - kBoxLeft, yy, frame, bar);
+                    tma_load_3d(dst + r * kBoxW, tmA1, it.bx - kBoxLeft, yy, it.frame, bar);
+                    tma_load_3d(dst + kImgStageBytes + r * kBoxW, tmB1, it.bx - kBoxLeft, yy, it.frame, bar);
                 }
             }
         }
     };
-
     #pragma unroll
     for (int s = 0; s < kStages; ++s)
-        if (s < nLoads) issue_load(s);
+        if (s < it.nBlk) issue_load(s);
 
-    // ---- per-item centring pixel: moments are accumulated on (a - ca), (b - cb), which keeps the fp32
-    // cancellation in E[x^2] - mu^2 small even on flat regions (DESIGN.md "Numerics").  Any integer works.
-    const int cx = min(bx + kBandW / 2, p.width - 1);
-    const int cy = min(max(oy0, 0), p.srcRows - 1);
-    const float ca = (float)__ldg(p.a + (long long)frame * p.frameStrideA + (long long)cy * p.pitchA + cx);
-    const float cb = (float)__ldg(p.b + (long long)frame * p.frameStrideB + (long long)cy * p.pitchB + cx);
+    // (a - ca, b - cb) from the bytes: PRMT builds 2^23 + byte, one packed FADD removes 2^23 + centre (exact)
     const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));
     const uint32_t magic = p.magic;                    // 0x4B000000, passed as a parameter so that it lives in a register and
                                                        // PRMT takes the byte selector as its immediate (no per-PRMT selector MOV)
-    const float k2     = -0.5f * p.eps2 * (ca - cb) * (ca - cb);                 // see the formula below
+    const float k2 = -0.5f * p.eps2 * (ca - cb) * (ca - cb);  // see the formula in consumer_warp()
 
-    // taps: w[m] multiplies the sample at offset m of an 11-sample window, w[m] = g[|m-5|]
     u64 w2[6];
     #pragma unroll
     for (int d = 0; d < 6; ++d) w2[d] = pack2(p.g[d], p.g[d]);
     #define TAP(m) w2[(m) < 5 ? 5 - (m) : (m) - 5]
 
-    // ---- horizontal-pass role of this lane: row hr of the block, 16 output columns starting at 16*hq
+    // this lane's share of a block: row hr, 16 output columns starting at 16*hq
     const int hr = lane >> 2, hq = lane & 3;
     const uint32_t hSrcOff  = hr * kBoxW + hq * 16 + (kBoxLeft - 8);              // 32-byte window holding columns 16hq-8 .. 16hq+23
-    const uint32_t hSwz     = (uint32_t)(hq | ((hr & 3) << 2)) << 3;              // ring swizzle (see ring layout below)
-    const uint32_t hDstBase = ringBase + hr * kRingRowBytes + hq * 128;
 
-    // ---- vertical-pass role: columns bx+lane and bx+32+lane.  Ring layout: row r holds two planes of 64 packed
-    // pairs, {mu_a', mu_b'} at +0 and {D, P} at +512; column c sits at 8*(c ^ ((c>>4) | ((r&3)<<2))).  The XOR makes
-    // both the 8-byte stores of the horizontal pass (lanes = 4 rows x 4 column groups per half-warp) and the 8-byte
-    // loads of the vertical pass (lanes = 16 adjacent columns per half-warp) bank-conflict free.
-    const uint32_t vBase0 = (uint32_t)(lane ^ (lane >> 4)) << 3;
-    const uint32_t vBase1 = (uint32_t)((32 + lane) ^ (2 + (lane >> 4))) << 3;
-    const bool colOk0 = bx + lane < p.width;
-    const bool colOk1 = bx + 32 + lane < p.width;
+    const bool patchLeft  = (it.bx == 0);
+    const bool patchRight = (it.bx + kBandW + kHalo > p.width);
 
-    // 11-deep shifted accumulators of the vertical pass: q[m] holds the partial sum of the output row that will
-    // complete m rows from now; per input row q[m] = fma(h, w[m], q[m+1]) and q[0] is a finished output.
-    u64 qab0[11], qsp0[11], qab1[11], qsp1[11];
-    #pragma unroll
-    for (int m = 0; m < 11; ++m) qab0[m] = qsp0[m] = qab1[m] = qsp1[m] = 0ull;
-
-    const bool patchLeft  = (bx == 0);
-    const bool patchRight = (bx + kBandW + kHalo > p.width);
-    // running map pointer: row of the output completed by the current input row (starts 10 rows above the segment;
-    // never dereferenced there)
-    float* mapPtr = nullptr;
-    if (kMap) mapPtr = p.map + (long long)frame * p.mapFrameStride + (long long)(oy0 - p.outY0 - 2 * kHalo) * p.mapPitch + bx + lane;
-
-    double total = 0.0;
+    int acquired = 0;      // ring halves (global count) this warp may write
+    int released = 0;      // ring halves (global count) handed to the consumer
 
     #pragma unroll 1
-    for (int blk = 0; blk < nBlk; ++blk) {
-        const int ld = blk >> 1, half = blk & 1;                        // TMA load and which 8 of its 16 rows
-        const uint32_t loadBase  = warpSmem + (ld & (kStages - 1)) * kStageBytes;
-        const uint32_t stageBase = loadBase + half * (kBlkRows * kBoxW);
+    for (int blk = 0; blk < it.nBlk; ++blk) {
+        const int stage = blk % kStages;
+        const uint32_t stageBase = pairSmem + stage * kStageBytes;
+        mbar_wait(barTma + 8 * stage, (uint32_t)(blk / kStages) & 1u);
 
-        if (half == 0) {
-            mbar_wait(barBase + 8 * (ld & (kStages - 1)), (uint32_t)(ld / kStages) & 1u);
-            if (patchLeft || patchRight) {                   // warp-uniform; only the outermost bands
-                const uint32_t row = loadBase + (lane >> 4) * kImgStageBytes + (lane & 15) * kBoxW;   // 2 images x 16 rows
+        if (patchLeft || patchRight) {                       // warp-uniform; only the outermost bands
+            if (lane < 2 * kLoadRows) {
+                const uint32_t row = stageBase + (lane >> 3) * kImgStageBytes + (lane & 7) * kBoxW;   // 2 images x 8 rows
                 if (patchLeft) {
                     uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row + kBoxLeft));
                     #pragma unroll
                     for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(row + kBoxLeft - k), "r"(v) : "memory");
                 }
                 if (patchRight) {
-                    const uint32_t last = row + kBoxLeft + (p.width - 1 - bx);
+                    const uint32_t last = row + kBoxLeft + (p.width - 1 - it.bx);
                     uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(last));
                     #pragma unroll
                     for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(last + k), "r"(v) : "memory");
                 }
-                __syncwarp();
             }
-        }
-
-        // ================================================================ horizontal pass: 8 rows x 64 columns
-        {
-            // the window starts 8 bytes into a 16-byte chunk: 8 + 16 + 8 byte loads
-            const uint2 a0 = lds64u(stageBase + hSrcOff), a2 = lds64u(stageBase + hSrcOff + 24);
-            const uint4 a1 = lds128(stageBase + hSrcOff + 8);
-            const uint2 b0 = lds64u(stageBase + kImgStageBytes + hSrcOff), b2 = lds64u(stageBase + kImgStageBytes + hSrcOff + 24);
-            const uint4 b1 = lds128(stageBase + kImgStageBytes + hSrcOff + 8);
-            const uint32_t wa[8] = {a0.x, a0.y, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
-            const uint32_t wb[8] = {b0.x, b0.y, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-            // every lane has read its inputs once the warp reconverges: after the second half the stage can be refilled
             __syncwarp();
-            if ((half == 1 || blk + 1 >= nBlk) && ld + kStages < nLoads) {
-                if (patchLeft || patchRight) fence_proxy_async();
-                issue_load(ld + kStages);
-            }
+        }
 
-            u64 hab[16], hsp[16];
+        // the window starts 8 bytes into a 16-byte chunk: 8 + 16 + 8 byte loads
+        const uint2 a0 = lds64u(stageBase + hSrcOff), a2 = lds64u(stageBase + hSrcOff + 24);
+        const uint4 a1 = lds128(stageBase + hSrcOff + 8);
+        const uint2 b0 = lds64u(stageBase + kImgStageBytes + hSrcOff), b2 = lds64u(stageBase + kImgStageBytes + hSrcOff + 24);
+        const uint4 b1 = lds128(stageBase + kImgStageBytes + hSrcOff + 8);
+        const uint32_t wa[8] = {a0.x, a0.y, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+        const uint32_t wb[8] = {b0.x, b0.y, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+        // every lane has read its inputs once the warp reconverges: the stage can be refilled
+        __syncwarp();
+        if (blk + kStages < it.nBlk) {
+            if (patchLeft || patchRight) fence_proxy_async();
+            issue_load(blk + kStages);
+        }
+
+        // Ring position of this lane's row: input row i = 8*blk + hr lives in half (i / 11) & 1 at row t = i % 11.
+        // Layout of a ring row: two planes of 64 packed pairs, {E_h[a'], E_h[b']} at +0 and {E_h[(a'-b')^2], E_h[a'b']} at
+        // +512; column c sits at 8*(c ^ ((c>>4) | ((t&3)<<2))).  The XOR makes both these 8-byte stores (lanes = 4 rows x
+        // 4 column groups per half-warp) and the consumer's 8-byte loads (16 adjacent columns per half-warp) conflict free.
+        const int i  = blk * kBlkRows + hr;
+        const int ih = i / kTaps, t = i - ih * kTaps;
+        const uint32_t hSwz    = (uint32_t)(hq | ((t & 3) << 2)) << 3;
+        const uint32_t dstBase = ringBase + (uint32_t)((ih & 1) * kTaps + t) * kRingRowBytes + hq * 128;
+
+        u64 hab[16], hsp[16];
+        #pragma unroll
+        for (int ii = 0; ii < 26; ++ii) {                // input column 16hq - 5 + ii  = byte 3 + ii of the 32-byte window
+            const int byteIdx = ii + 3;
+            float fa, fb;
+            switch (byteIdx & 3) {
+                case 0:  fa = magic_byte<0>(wa[byteIdx >> 2], magic); fb = magic_byte<0>(wb[byteIdx >> 2], magic); break;
+                case 1:  fa = magic_byte<1>(wa[byteIdx >> 2], magic); fb = magic_byte<1>(wb[byteIdx >> 2], magic); break;
+                case 2:  fa = magic_byte<2>(wa[byteIdx >> 2], magic); fb = magic_byte<2>(wb[byteIdx >> 2], magic); break;
+                default: fa = magic_byte<3>(wa[byteIdx >> 2], magic); fb = magic_byte<3>(wb[byteIdx >> 2], magic); break;
+            }
+            const u64 ab = add2(pack2(fa, fb), negMagic);          // (a - ca, b - cb), exact
+            float a, b; unpack2(ab, a, b);
+            const float d = a - b;
+            const u64 sp = pack2(fmaf(d, d, k2), a * b);           // ((a'-b')^2 + k2, a'b')
             #pragma unroll
-            for (int i = 0; i < 26; ++i) {                   // input column 16hq - 5 + i  = byte 3 + i of the 32-byte window
-                const int byteIdx = i + 3;
-                float fa, fb;
-                switch (byteIdx & 3) {
-                    case 0:  fa = magic_byte<0>(wa[byteIdx >> 2], magic); fb = magic_byte<0>(wb[byteIdx >> 2], magic); break;
-                    case 1:  fa = magic_byte<1>(wa[byteIdx >> 2], magic); fb = magic_byte<1>(wb[byteIdx >> 2], magic); break;
-                    case 2:  fa = magic_byte<2>(wa[byteIdx >> 2], magic); fb = magic_byte<2>(wb[byteIdx >> 2], magic); break;
-                    default: fa = magic_byte<3>(wa[byteIdx >> 2], magic); fb = magic_byte<3>(wb[byteIdx >> 2], magic); break;
+            for (int j = 0; j < 16; ++j) {
+                const int k = ii - j;                               // sample ii is tap k of output j
+                if (k == 0)                { hab[j] = mul2(ab, TAP(0)); hsp[j] = mul2(sp, TAP(0)); }
+                else if (k > 0 && k <= 10) { hab[j] = fma2(ab, TAP(k), hab[j]); hsp[j] = fma2(sp, TAP(k), hsp[j]); }
+            }
+            if (ii == 10) {
+                // first store of the block: the ring halves this block touches must have been drained by the consumer
+                // (waiting here, not at the top, lets the loads and the first 10 columns of math overlap the wait)
+                const int lastHalf = (blk * kBlkRows + kBlkRows - 1) / kTaps;
+                while (acquired <= lastHalf) {
+                    mbar_wait_sleep(barEmpty + 8 * (acquired & 1), ((uint32_t)(acquired >> 1) & 1u) ^ 1u);
+                    ++acquired;
                 }
-                const u64 ab = add2(pack2(fa, fb), negMagic);          // (a - ca, b - cb), exact
-                float a, b; unpack2(ab, a, b);
-                const float d = a - b;
-                const u64 sp = pack2(fmaf(d, d, k2), a * b);           // ((a'-b')^2 + k2, a'b'); k2: see the formula below
-                #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int k = i - j;                                // sample i is tap k of output j
-                    if (k == 0)                { hab[j] = mul2(ab, TAP(0)); hsp[j] = mul2(sp, TAP(0)); }
-                    else if (k > 0 && k <= 10) { hab[j] = fma2(ab, TAP(k), hab[j]); hsp[j] = fma2(sp, TAP(k), hsp[j]); }
-                }
-                if (i >= 10) {                                          // output j = i-10 is complete
-                    const int j = i - 10;
-                    const uint32_t dst = hDstBase + ((uint32_t)(j << 3) ^ hSwz);
-                    sts64(dst, hab[j]);
-                    sts64(dst + kRingPlaneBytes, hsp[j]);
-                }
+            }
+            if (ii >= 10) {                                         // output j = ii-10 is complete
+                const int j = ii - 10;
+                const uint32_t dst = dstBase + ((uint32_t)(j << 3) ^ hSwz);
+                sts64(dst, hab[j]);
+                sts64(dst + kRingPlaneBytes, hsp[j]);
             }
         }
-        __syncwarp();
+        __syncwarp();                                               // all 32 lanes' stores precede the (releasing) arrives
+        const int complete = (blk * kBlkRows + kBlkRows) / kTaps;   // ring halves fully written so far
+        if (lane == 0) {
+            for (int hdone = released; hdone < complete; ++hdone) mbar_arrive(barFull + 8 * (hdone & 1));
+        }
+        released = max(released, complete);
+    }
+    #undef TAP
+}
 
-        // ================================================================ vertical pass + formula: 8 rows x 2 columns per lane
-        float blockSum = 0.f;
+// ---- consumer: vertical pass + formula + outputs
+template <bool kMap>
+__device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCoords& it, int lane, long long item, uint32_t pairSmem,
+                                              uint32_t barFull, uint32_t barEmpty, float ca, float cb)
+{
+    const uint32_t ringBase = pairSmem + kStages * kStageBytes;
+    u64 w2[6];
+    #pragma unroll
+    for (int d = 0; d < 6; ++d) w2[d] = pack2(p.g[d], p.g[d]);
+    #define TAP(m) w2[(m) < 5 ? 5 - (m) : (m) - 5]
+    constexpr float c1 = 6.5025f, c2 = 58.5225f;          // (0.01*255)^2, (0.03*255)^2 as float: src/ssim.cpp:956-960
+
+    // this lane owns columns bx+lane and bx+32+lane (ring layout: see producer_warp)
+    const uint32_t vBase0 = (uint32_t)(lane ^ (lane >> 4)) << 3;
+    const uint32_t vBase1 = (uint32_t)((32 + lane) ^ (2 + (lane >> 4))) << 3;
+    const bool colOk0 = it.bx + lane < p.width;
+    const bool colOk1 = it.bx + 32 + lane < p.width;
+
+    // Eleven in-place accumulators per plane pair and column: slot s accumulates the output row whose first input row
+    // is == s (mod 11).  At row t of a body slot s receives tap (t - s) mod 11; the slot receiving tap 0 is re-initialised,
+    // the slot receiving tap 10 is complete.  All indices are compile-time constants.
+    u64 qab0[kTaps], qsp0[kTaps], qab1[kTaps], qsp1[kTaps];
+    #pragma unroll
+    for (int m = 0; m < kTaps; ++m) qab0[m] = qsp0[m] = qab1[m] = qsp1[m] = 0ull;
+
+    // running map pointer: row of the output completed by the current input row (starts 10 rows above the segment;
+    // never dereferenced there)
+    float* mapPtr = nullptr;
+    if (kMap) mapPtr = p.map + (long long)it.frame * p.mapFrameStride + (long long)(it.oy0 - p.outY0 - 2 * kHalo) * p.mapPitch + it.bx + lane;
+
+    const int nRows = it.nOut + 2 * kHalo;                              // input rows that complete a wanted output
+    double total = 0.0;
+
+    #pragma unroll 1
+    for (int body = 0; body < it.nBodies; ++body) {
+        const uint32_t halfBase = ringBase + (uint32_t)(body & 1) * (kTaps * kRingRowBytes);
+        mbar_wait_sleep(barFull + 8 * (body & 1), (uint32_t)(body >> 1) & 1u);
+        const int iBase = body * kTaps;
+        float bodySum = 0.f;
         #pragma unroll
-        for (int r = 0; r < kBlkRows; ++r) {
-            const uint32_t row0 = ringBase + r * kRingRowBytes + (vBase0 ^ ((r & 3) << 5));
-            const uint32_t row1 = ringBase + r * kRingRowBytes + (vBase1 ^ ((r & 3) << 5));
-            const u64 hab0 = lds64(row0), hsp0 = lds64(row0 + kRingPlaneBytes);
-            const u64 hab1 = lds64(row1), hsp1 = lds64(row1 + kRingPlaneBytes);
+        for (int t = 0; t < kTaps; ++t) {
+            const uint32_t rowB = halfBase + t * kRingRowBytes;
+            const uint32_t sw   = (uint32_t)(t & 3) << 5;
+            const u64 hab0 = lds64(rowB + (vBase0 ^ sw)), hsp0 = lds64(rowB + (vBase0 ^ sw) + kRingPlaneBytes);
+            const u64 hab1 = lds64(rowB + (vBase1 ^ sw)), hsp1 = lds64(rowB + (vBase1 ^ sw) + kRingPlaneBytes);
             #pragma unroll
-            for (int m = 0; m < 10; ++m) {
-                qab0[m] = fma2(hab0, TAP(m), qab0[m + 1]);
-                qsp0[m] = fma2(hsp0, TAP(m), qsp0[m + 1]);
-                qab1[m] = fma2(hab1, TAP(m), qab1[m + 1]);
-                qsp1[m] = fma2(hsp1, TAP(m), qsp1[m + 1]);
+            for (int s = 0; s < kTaps; ++s) {
+                const int k = (t - s + kTaps) % kTaps;
+                if (k == 0) {
+                    qab0[s] = mul2(hab0, TAP(0)); qsp0[s] = mul2(hsp0, TAP(0));
+                    qab1[s] = mul2(hab1, TAP(0)); qsp1[s] = mul2(hsp1, TAP(0));
+                } else {
+                    qab0[s] = fma2(hab0, TAP(k), qab0[s]); qsp0[s] = fma2(hsp0, TAP(k), qsp0[s]);
+                    qab1[s] = fma2(hab1, TAP(k), qab1[s]); qsp1[s] = fma2(hsp1, TAP(k), qsp1[s]);
+                }
             }
-            qab0[10] = mul2(hab0, TAP(10)); qsp0[10] = mul2(hsp0, TAP(10));
-            qab1[10] = mul2(hab1, TAP(10)); qsp1[10] = mul2(hsp1, TAP(10));
+            if (t == kTaps - 1) {                                       // the ring half has been read completely
+                __syncwarp();
+                if (lane == 0) mbar_arrive(barEmpty + 8 * (body & 1));
+            }
 
-            // Output row (segment-relative) completed by this input row.  The formula is evaluated unconditionally (rows
-            // outside [0,nOut) only cost the pipeline fill) so that its dependent chain overlaps the next row's FMAs
-            // instead of sitting behind a branch; only the store and the sum are predicated.
-            const int o = blk * kBlkRows + r - 2 * kHalo;
-            const bool rowOk = (o >= 0) && (o < nOut);
-            float s[2];
+            // Output row completed by this input row.  The formula is evaluated unconditionally (the first 10 rows of a
+            // segment and the filler rows at its end only cost the pipeline fill); the store and the sum are predicated.
+            const int done = (t + 1) % kTaps;
+            const int i = iBase + t;
+            const bool rowOk = (i >= 2 * kHalo) && (i < nRows);
+            float sv[2];
             #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 float ma, mb, D, P;
-                unpack2(c == 0 ? qab0[0] : qab1[0], ma, mb);
-                unpack2(c == 0 ? qsp0[0] : qsp1[0], D, P);
+                unpack2(c == 0 ? qab0[done] : qab1[done], ma, mb);
+                unpack2(c == 0 ? qsp0[done] : qsp1[done], D, P);
                 // The reference formula (src/ssim.cpp:590-704) rearranged so that numerator and denominator share
                 // their terms:  mu_a^2 + mu_b^2 = 2 mu_a mu_b + (mu_a - mu_b)^2  and
                 // sigma_a^2 + sigma_b^2 = 2 sigma_ab + var(a - b),  var(a-b) = E[(a'-b')^2] - (E[a'] - E[b'])^2.
@@ -298,32 +361,31 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
                 // The reference's window sums to 1+eps (see gaussian_taps() in ssim_cuda.cu), which on its RAW moments
                 // shifts every covariance by -eps*mu_a*mu_b; centred moments only see -eps*ma*mb, so the difference
                 // -eps*(mu_a mu_b - ma mb) is applied explicitly (the matching -eps*(ca-cb)^2 of var(a-b) is already
-                // inside D: k2 was added to every (a'-b')^2 before the blur, for free, by turning an FMUL into an FFMA).
+                // inside D: the producer added k2 to every (a'-b')^2 before the blur, turning an FMUL into an FFMA).
                 const float mua = ma + ca, mub = mb + cb;
-                const float t   = mua * mub;
-                const float n1  = fmaf(2.f, t, p.c1);
+                const float tt  = mua * mub;
+                const float n1  = fmaf(2.f, tt, c1);
                 const float dmu = mua - mub;
                 const float d1  = fmaf(dmu, dmu, n1);
-                const float n2  = fmaf(-p.eps2, fmaf(-ma, mb, t), fmaf(2.f, fmaf(-ma, mb, P), p.c2));
+                const float n2  = fmaf(-p.eps2, fmaf(-ma, mb, tt), fmaf(2.f, fmaf(-ma, mb, P), c2));
                 const float dm  = ma - mb;
                 const float d2  = n2 + fmaf(-dm, dm, D);
                 const float num = n1 * n2, den = d1 * d2;
-                // den >= c1*c2 > 0 on valid rows.  MUFU.RCP + one Newton step on the quotient: ~correctly rounded, exact
-                // when num == den
+                // den >= c1*c2 > 0 on valid rows.  MUFU.RCP + one Newton step on the quotient: ~correctly rounded,
+                // exact when num == den
                 float rc; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));
                 const float q = num * rc;
-                s[c] = fmaf(rc, fmaf(-q, den, num), q);
+                sv[c] = fmaf(rc, fmaf(-q, den, num), q);
             }
             const bool ok0 = rowOk && colOk0, ok1 = rowOk && colOk1;
             if (kMap) {
-                if (ok0) mapPtr[0]  = s[0];
-                if (ok1) mapPtr[32] = s[1];
+                if (ok0) mapPtr[0]  = sv[0];
+                if (ok1) mapPtr[32] = sv[1];
                 mapPtr += p.mapPitch;
             }
-            blockSum += (ok0 ? s[0] : 0.f) + (ok1 ? s[1] : 0.f);
+            bodySum += (ok0 ? sv[0] : 0.f) + (ok1 ? sv[1] : 0.f);
         }
-        total += (double)blockSum;                                      // <= 16 values per float partial
-        __syncwarp();                                                   // ring is rewritten by the next horizontal pass
+        total += (double)bodySum;                                       // <= 22 values per float partial
     }
     #undef TAP
 
@@ -331,6 +393,49 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
     if (lane == 0) p.partials[item] = total;
+}
+
+template <bool kMap>
+__global__ void __launch_bounds__(kCtaThreads, 2)
+ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB8, const __grid_constant__ CUtensorMap tmB1,
+                  const __grid_constant__ FusedParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[kPairsPerCta][8];            // per pair: tmaFull[3], (pad), ringFull[2], ringEmpty[2]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int pair = warp & (kPairsPerCta - 1);
+    const bool isConsumer = warp >= kPairsPerCta;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPairsPerCta * 8; ++i) mbar_init(smem_u32(&bars[0][0]) + 8 * i, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();                                                    // the only CTA-wide barrier
+
+    const long long item = (long long)blockIdx.x * kPairsPerCta + pair;
+    const uint32_t pairSmem = smem_u32(smem) + pair * kPairSmemBytes;
+    const uint32_t barBase  = smem_u32(&bars[pair][0]);
+
+    // Register hand-over between the two warpgroups: every warp of a warpgroup must execute its setmaxnreg (so it comes
+    // before the early exit), and each role's code must follow its own setmaxnreg within the same branch -- ptxas budgets
+    // registers per region, and any code shared by both roles would be held to the smaller budget.
+    if (isConsumer) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kConsumerRegs));
+        if (item >= p.items) return;
+        ItemCoords it; float ca, cb;
+        decode_item(p, item, it, ca, cb);
+        consumer_warp<kMap>(p, it, lane, item, pairSmem, barBase + 32, barBase + 48, ca, cb);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kProducerRegs));
+        if (item >= p.items) return;
+        ItemCoords it; float ca, cb;
+        decode_item(p, item, it, ca, cb);
+        producer_warp(&tmA8, &tmA1, &tmB8, &tmB1, p, it, lane, pairSmem, barBase, barBase + 32, barBase + 48, ca, cb);
+    }
 }
 
 // Sums the per-item partials of each frame in a fixed order (deterministic), writes the double sum and
@@ -400,10 +505,10 @@ static cudaError_t set_smem_attr()
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA8, const CUtensorMap& tmA1,
                          const CUtensorMap& tmB8, const CUtensorMap& tmB1, const FusedParams& p)
 {
-    const long long ctas = (p.items + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long ctas = (p.items + kPairsPerCta - 1) / kPairsPerCta;
     if (ctas <= 0 || ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (p.map) ssim_fused_kernel<true><<<(unsigned)ctas, kWarpsPerCta * 32, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
-    else       ssim_fused_kernel<false><<<(unsigned)ctas, kWarpsPerCta * 32, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
+    if (p.map) ssim_fused_kernel<true><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
+    else       ssim_fused_kernel<false><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
     return cudaGetLastError();
 }
 
@@ -423,7 +528,7 @@ cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm
     if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<false>)) != cudaSuccess) return e;
     if (regsNoMap) *regsNoMap = fa.numRegs;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<true>, kWarpsPerCta * 32, kCtaSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<true>, kCtaThreads, kCtaSmemBytes);
     if (ctasPerSm) *ctasPerSm = n;
     return e;
 }

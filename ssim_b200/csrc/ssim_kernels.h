@@ -17,16 +17,21 @@ constexpr int kBoxW        = 128;  // TMA box width in bytes: 16 left margin + 6
 constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row: the innermost TMA coordinate (bx - 16) must be
                                    // a multiple of 16 bytes -- measured on B200: x = -16 works, x = -8 raises "illegal instruction"
                                    // (tools/dev/tma_probe.cu)
-constexpr int kLoadRows    = 16;   // rows per TMA box: two blocks per load halves the (warp-wide) TMA issue overhead
-constexpr int kStages      = 2;    // TMA ring depth per warp (16-row loads)
-constexpr int kWarpsPerCta = 4;
-constexpr int kImgStageBytes = kBoxW * kLoadRows;        // 2048
-constexpr int kStageBytes    = 2 * kImgStageBytes;       // 4096 (A then B)
+constexpr int kLoadRows    = 8;    // rows per TMA box (= one horizontal-pass block)
+constexpr int kStages      = 3;    // TMA ring depth per work item
+constexpr int kPairsPerCta = 4;    // work items per CTA: each is served by one producer warp and one consumer warp
+constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 256: warps 0-3 producers (TMA + horizontal pass), 4-7 consumers
+constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
+constexpr int kConsumerRegs = 160;
+constexpr int kImgStageBytes = kBoxW * kLoadRows;        // 1024
+constexpr int kStageBytes    = 2 * kImgStageBytes;       // 2048 (A then B)
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
 constexpr int kRingRowBytes   = 2 * kRingPlaneBytes;     // 1024: {E[a'], E[b']} plane then {E[(a'-b')^2], E[a'b']} plane
-constexpr int kRingBytes      = kBlkRows * kRingRowBytes; // 8192: horizontal-pass output of one block
-constexpr int kWarpSmemBytes = kStages * kStageBytes + kRingBytes;  // 16384
-constexpr int kCtaSmemBytes  = kWarpsPerCta * kWarpSmemBytes;       // 65536 -> 3 CTAs (12 warps) per SM
+constexpr int kTaps           = 11;
+constexpr int kRingRows       = 2 * kTaps;               // 22: two halves of 11 rows; the consumer's unrolled body is 11 rows
+constexpr int kRingBytes      = kRingRows * kRingRowBytes; // 22528
+constexpr int kPairSmemBytes = kStages * kStageBytes + kRingBytes;  // 28672
+constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;       // 114688 -> 2 CTAs (16 warps) per SM
 
 struct FusedParams {
     const uint8_t* a;        // raw planes (used only to fetch the per-item centring pixel)

@@ -1,0 +1,26 @@
+import sys; sys.path.insert(0,'/root/repo')
+import torch, statistics
+from ssim_b200 import api
+lib=api.cuda_lib()
+st=torch.cuda.current_stream(); sh=st.cuda_stream
+def run(W,H,frames,with_map,seg,iters=30):
+    a=torch.empty((frames,H,W),dtype=torch.uint8,device='cuda'); b=torch.empty_like(a)
+    m=torch.empty((frames,H,W),dtype=torch.float32,device='cuda') if with_map else None
+    sums=torch.empty(frames,dtype=torch.float64,device='cuda')
+    for f in range(frames): api.synth_fill(0,sh,a[f].data_ptr(),W,b[f].data_ptr(),W,W,H,0,f)
+    lib.ssim_cuda_set_segment_rows(seg)
+    ts=[]
+    for i in range(iters+3):
+        e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        api.compute_device(0,sh,W,H,0,H,frames,a.data_ptr(),W,W*H,b.data_ptr(),W,W*H,m.data_ptr() if with_map else None,W,W*H,sums.data_ptr(),None)
+        e1.record(st); torch.cuda.synchronize()
+        if i>=3: ts.append(e0.elapsed_time(e1)*1e3)
+    lib.ssim_cuda_set_segment_rows(0)
+    return statistics.median(ts)
+for seg in [0,54,64,75,90,108,135,180,270]:
+    print("4K single map seg",seg, "us", round(run(3840,2160,1,True,seg),1))
+for seg in [0,19,27,36,45,60,90,135]:
+    print("1080p single nomap seg",seg,"us", round(run(1920,1080,1,False,seg),1))
+for seg in [0,256,512,1024,2048]:
+    t=run(16384,16384,1,True,seg,8); print("16k seg",seg,"us",round(t,1),"Mpix/s",round(16384*16384/t,1))
