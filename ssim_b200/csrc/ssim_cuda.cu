@@ -304,6 +304,10 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.c2 = (float)((0.03 * 255) * (0.03 * 255));
     p.magic = 0x4B000000u;
     {
+        static const unsigned backoff = [] { const char* e = getenv("SSIM_CUDA_BACKOFF_NS"); return e ? (unsigned)atoi(e) : ssimk::kBackoffNs; }();
+        p.backoffNs = backoff;
+    }
+    {
         double s1 = (double)c->taps[0];
         for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];
         p.eps2 = (float)(2.0 * (s1 * s1 - 1.0));

@@ -99,17 +99,21 @@ struct ItemCoords {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
-// try_wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots in a spin loop
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+// Waiting on the partner warp: poll once, then back off with an explicit nanosleep between polls.  (try_wait's own
+// suspend-time hint compiles to a NANOSLEEP.SYNCS loop that re-polls almost immediately: 19% of all issued instructions
+// in the first profile of this kernel were that loop.)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" :: "r"(bar), "r"(parity), "r"(2000u) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned backoffNs) {
+    while (!mbar_test(bar, parity)) __nanosleep(backoffNs);
 }
 
 // (frame, segment, band) of a work item, band fastest so that a CTA covers 4 adjacent bands; plus the per-item centring
@@ -261,7 +265,7 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
                 // (waiting here, not at the top, lets the loads and the first 10 columns of math overlap the wait)
                 const int lastHalf = (blk * kBlkRows + kBlkRows - 1) / kTaps;
                 while (acquired <= lastHalf) {
-                    mbar_wait_sleep(barEmpty + 8 * (acquired & 1), ((uint32_t)(acquired >> 1) & 1u) ^ 1u);
+                    mbar_wait_sleep(barEmpty + 8 * (acquired & 1), ((uint32_t)(acquired >> 1) & 1u) ^ 1u, p.backoffNs);
                     ++acquired;
                 }
             }
@@ -318,7 +322,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
     #pragma unroll 1
     for (int body = 0; body < it.nBodies; ++body) {
         const uint32_t halfBase = ringBase + (uint32_t)(body & 1) * (kTaps * kRingRowBytes);
-        mbar_wait_sleep(barFull + 8 * (body & 1), (uint32_t)(body >> 1) & 1u);
+        mbar_wait_sleep(barFull + 8 * (body & 1), (uint32_t)(body >> 1) & 1u, p.backoffNs);
         const int iBase = body * kTaps;
         float bodySum = 0.f;
         #pragma unroll

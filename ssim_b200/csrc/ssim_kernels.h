@@ -23,6 +23,7 @@ constexpr int kPairsPerCta = 4;    // work items per CTA: each is served by one 
 constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 256: warps 0-3 producers (TMA + horizontal pass), 4-7 consumers
 constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
 constexpr int kConsumerRegs = 160;
+constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partner warp's mbarrier
 constexpr int kImgStageBytes = kBoxW * kLoadRows;        // 1024
 constexpr int kStageBytes    = 2 * kImgStageBytes;       // 2048 (A then B)
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
@@ -46,6 +47,7 @@ struct FusedParams {
     float g[6];              // separable 11-tap weights: g[d] is the tap at distance d from the centre
     float c1, c2;
     uint32_t magic;          // 0x4B000000 (float 2^23): kept opaque to ptxas, see the kernel
+    uint32_t backoffNs;      // sleep between polls of the partner warp's mbarrier
     float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
 };
 

@@ -9,11 +9,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 template <int RANK>
-__global__ void probe(const __grid_constant__ CUtensorMap tm, int x, int y, int boxBytes, uint8_t* out)
+__global__ void probe(const __grid_constant__ CUtensorMap tm, int x, int y, int boxBytes, uint8_t* out, int dstOff)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    uint32_t b = smem_u32(&bar), d = smem_u32(smem);
+    uint32_t b = smem_u32(&bar), d = smem_u32(smem) + dstOff;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -30,7 +30,7 @@ __global__ void probe(const __grid_constant__ CUtensorMap tm, int x, int y, int 
                          :: "r"(d), "l"(&tm), "r"(x), "r"(y), "r"(b) : "memory");
     }
     asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}\n" :: "r"(b), "r"(0) : "memory");
-    for (int i = threadIdx.x; i < boxBytes; i += blockDim.x) out[i] = smem[i];
+    for (int i = threadIdx.x; i < boxBytes; i += blockDim.x) out[i] = smem[i + dstOff];
 }
 int main()
 {
@@ -42,9 +42,8 @@ int main()
     std::vector<uint8_t> h(pitch * H);
     for (int y = 0; y < H; ++y) for (int x = 0; x < pitch; ++x) h[y * pitch + x] = (uint8_t)(x * 7 + y * 13);
     uint8_t *d, *out; cudaMalloc(&d, pitch * H); cudaMalloc(&out, 4096); cudaMemcpy(d, h.data(), pitch * H, cudaMemcpyHostToDevice);
-    struct Case { int rank, boxW, boxH, x, y; };
-    Case cases[] = {{2, 128, 8, -16, 16}, {2, 128, 8, 16, -3}, {2, 80, 8, -16, 136}, {3, 128, 8, -16, 16}, {3, 128, 1, 304, 140}, {3, 96, 8, 48, 8},
-                    {2, 128, 8, 8, 16}, {2, 128, 8, 4, 16}};
+    struct Case { int rank, boxW, boxH, x, y, off; };
+    Case cases[] = {{3, 64, 16, -16, 8, 0}, {3, 64, 1, 16, 5, 64}, {3, 64, 1, 16, 5, 192}, {3, 64, 1, -16, 140, 16}, {3, 64, 1, -16, 140, 32}, {3, 128, 1, 0, 3, 80}};
     for (Case c : cases) {
         CUtensorMap tm;
         cuuint64_t dims[3] = {W, H, 1}; cuuint64_t strides[2] = {pitch, (cuuint64_t)pitch * H};
@@ -53,7 +52,7 @@ int main()
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         int bytes = c.boxW * c.boxH;
         cudaMemset(out, 0xEE, 4096);
-        if (c.rank == 3) probe<3><<<1, 32, 4096>>>(tm, c.x, c.y, bytes, out); else probe<2><<<1, 32, 4096>>>(tm, c.x, c.y, bytes, out);
+        if (c.rank == 3) probe<3><<<1, 32, 4096>>>(tm, c.x, c.y, bytes, out, c.off); else probe<2><<<1, 32, 4096>>>(tm, c.x, c.y, bytes, out, c.off);
         cudaError_t e = cudaDeviceSynchronize();
         std::vector<uint8_t> o(bytes); cudaMemcpy(o.data(), out, bytes, cudaMemcpyDeviceToHost);
         int bad = 0;
@@ -61,7 +60,7 @@ int main()
             int xx = c.x + k, yy = c.y + r2; uint8_t want = (xx < 0 || xx >= W || yy < 0 || yy >= H) ? 0 : h[yy * pitch + xx];
             if (o[r2 * c.boxW + k] != want) ++bad;
         }
-        printf("rank %d box %dx%d at (%d,%d): encode=%d run=%s mismatches=%d\n", c.rank, c.boxW, c.boxH, c.x, c.y, (int)r, cudaGetErrorString(e), bad);
+        printf("rank %d box %dx%d at (%d,%d) smem+%d: encode=%d run=%s mismatches=%d\n", c.rank, c.boxW, c.boxH, c.x, c.y, c.off, (int)r, cudaGetErrorString(e), bad);
         if (e != cudaSuccess) { printf("sticky error, stopping\n"); return 1; }
     }
     return 0;
