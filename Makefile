@@ -10,7 +10,9 @@ CSRC    := ssim_b200/csrc
 LIB     := ssim_b200/lib
 OBJ     := build/obj
 
-all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so
+BIN     := ssim_b200/bin
+
+all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so $(BIN)/rmgr-ssim
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/ssim_kernels.h $(CSRC)/synth.h include/ssim_cuda.h
 	@mkdir -p $(OBJ)
@@ -27,10 +29,15 @@ $(LIB)/libssim_cuda.so: $(OBJ)/ssim_kernels.o $(OBJ)/ssim_cuda.o
 $(LIB)/librmgr-ssim.so: $(OBJ)/rmgr_api.o $(LIB)/libssim_cuda.so
 	$(HOSTCXX) -shared -o $@ $(OBJ)/rmgr_api.o -L$(LIB) -lssim_cuda -Wl,-rpath,'$$ORIGIN'
 
+# rmgr-ssim: the reference's CLI (src/ssim-cli.cpp) re-done on top of the public API; PNG/PNM I/O via zlib
+$(BIN)/rmgr-ssim: $(CSRC)/ssim_cli.cpp $(LIB)/librmgr-ssim.so $(LIB)/libssim_cuda.so
+	@mkdir -p $(BIN)
+	$(HOSTCXX) -O2 -std=c++17 -Iinclude -o $@ $(CSRC)/ssim_cli.cpp -L$(LIB) -lrmgr-ssim -lssim_cuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(BIN)
 
 .PHONY: all oracle clean

@@ -59,6 +59,17 @@ int ssim_cuda_compute(int device, uint32_t width, uint32_t height,
                       float* ssim);
 
 /*
+ * SSIM of the BT.601 luma of two interleaved RGB(A) images: rgb points at the R byte of pixel (0,0), step >= 3 is the
+ * distance between pixels.  The luma planes ((19595 R + 38470 G + 7471 B + 32768) >> 16, the integer formula of the
+ * reference CLI, src/ssim-cli.cpp:158-186) are produced on the GPU.  Otherwise like ssim_cuda_compute().  Blocking.
+ */
+int ssim_cuda_compute_luma(int device, uint32_t width, uint32_t height,
+                           const uint8_t* rgbA, ptrdiff_t stepA, ptrdiff_t strideA,
+                           const uint8_t* rgbB, ptrdiff_t stepB, ptrdiff_t strideB,
+                           float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                           float* ssim);
+
+/*
  * Device-resident planes, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
  * stream).  `frames` independent pairs are processed by ONE kernel launch (+ one small reduction launch).
  *

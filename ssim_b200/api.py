@@ -44,6 +44,8 @@ def cuda_lib():
     lib.ssim_cuda_compute.argtypes = [C.c_int, C.c_uint32, C.c_uint32, u8p, C.c_ssize_t, C.c_ssize_t, u8p, C.c_ssize_t, C.c_ssize_t,
                                       f32p, C.c_ssize_t, C.c_ssize_t, C.POINTER(C.c_float)]
     lib.ssim_cuda_compute.restype = C.c_int
+    lib.ssim_cuda_compute_luma.argtypes = lib.ssim_cuda_compute.argtypes
+    lib.ssim_cuda_compute_luma.restype = C.c_int
     lib.ssim_cuda_compute_device.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                              u8p, C.c_size_t, C.c_size_t, u8p, C.c_size_t, C.c_size_t,
                                              f32p, C.c_size_t, C.c_size_t, f64p, f32p]

@@ -341,11 +341,17 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Brings one strided image into a canonical plane (dense rows, 16-byte aligned pitch) in device memory.
 // On return *plane/*pitch describe it; it is either the caller's own memory (already canonical) or ctx scratch.
 int canonical_plane(Context* c, cudaStream_t s, const uint8_t* img, ptrdiff_t step, ptrdiff_t stride, uint32_t W, uint32_t H,
-                    Buffer& planeBuf, Buffer& rawBuf, const uint8_t** plane, size_t* pitch)
+                    Buffer& planeBuf, Buffer& rawBuf, const uint8_t** plane, size_t* pitch, bool luma = false)
 {
+    // luma: `img` points at the R byte of interleaved RGB(A) pixels, three channels are read per pixel
+    auto pack = [&](uint8_t* dst, long long dstPitch, const uint8_t* src, long long st, long long sd) {
+        return luma ? ssimk::launch_pack_luma(s, dst, dstPitch, src, st, sd, (int)W, (int)H)
+                    : ssimk::launch_pack_u8(s, dst, dstPitch, src, st, sd, (int)W, (int)H);
+    };
+    const ptrdiff_t extra = luma ? 2 : 0;                      // bytes read beyond the addressed one
     const Where where = classify(img);
     const size_t canonPitch = align_up(W, 16);
-    if (where == Where::Device && step == 1 && stride >= (ptrdiff_t)W && (stride & 15) == 0 && ((uintptr_t)img & 15) == 0) {
+    if (!luma && where == Where::Device && step == 1 && stride >= (ptrdiff_t)W && (stride & 15) == 0 && ((uintptr_t)img & 15) == 0) {
         *plane = img; *pitch = (size_t)stride;
         return 0;
     }
@@ -353,20 +359,20 @@ int canonical_plane(Context* c, cudaStream_t s, const uint8_t* img, ptrdiff_t st
     if (rc) return rc;
     uint8_t* dst = (uint8_t*)planeBuf.ptr;
     *plane = dst; *pitch = canonPitch;
-    if (where == Where::Host && step == 1 && stride >= (ptrdiff_t)W) {
+    if (!luma && where == Where::Host && step == 1 && stride >= (ptrdiff_t)W) {
         CU_TRY(cudaMemcpy2DAsync(dst, canonPitch, img, (size_t)stride, W, H, cudaMemcpyHostToDevice, s));
         return 0;
     }
     if (where == Where::Device) {
-        CU_TRY(ssimk::launch_pack_u8(s, dst, (long long)canonPitch, img, step, stride, (int)W, (int)H));
+        CU_TRY(pack(dst, (long long)canonPitch, img, step, stride));
         return 0;
     }
     // host image with a general layout (interleaved channels, bottom-up, column-major ...): copy the byte range that
     // contains every addressed pixel, then gather on the device.
     const ptrdiff_t xExt = (ptrdiff_t)(W - 1) * step, yExt = (ptrdiff_t)(H - 1) * stride;
     const ptrdiff_t lo = std::min<ptrdiff_t>(0, xExt) + std::min<ptrdiff_t>(0, yExt);
-    const ptrdiff_t hi = std::max<ptrdiff_t>(0, xExt) + std::max<ptrdiff_t>(0, yExt);
-    const size_t span = (size_t)(std::abs(xExt)) + 1;             // bytes touched in one row
+    const ptrdiff_t hi = std::max<ptrdiff_t>(0, xExt) + std::max<ptrdiff_t>(0, yExt) + extra;
+    const size_t span = (size_t)(std::abs(xExt)) + 1 + (size_t)extra;   // bytes touched in one row
     const size_t absStride = (size_t)std::abs(stride);
     if (absStride >= span && H > 1) {
         // row-major-like: 2-D copy of H rows of `span` bytes
@@ -375,13 +381,13 @@ int canonical_plane(Context* c, cudaStream_t s, const uint8_t* img, ptrdiff_t st
         const uint8_t* firstRow = img + std::min<ptrdiff_t>(0, xExt) + std::min<ptrdiff_t>(0, yExt);   // lowest row start
         CU_TRY(cudaMemcpy2DAsync(rawBuf.ptr, rawPitch, firstRow, absStride, span, H, cudaMemcpyHostToDevice, s));
         // device address of pixel (0,0): row index in the copy is y (stride>0) or H-1-y (stride<0)
-        const uint8_t* d0 = (const uint8_t*)rawBuf.ptr + (stride < 0 ? (size_t)(H - 1) * rawPitch : 0) + (step < 0 ? span - 1 : 0);
-        CU_TRY(ssimk::launch_pack_u8(s, dst, (long long)canonPitch, d0, step, stride < 0 ? -(long long)rawPitch : (long long)rawPitch, (int)W, (int)H));
+        const uint8_t* d0 = (const uint8_t*)rawBuf.ptr + (stride < 0 ? (size_t)(H - 1) * rawPitch : 0) + (step < 0 ? span - 1 - (size_t)extra : 0);
+        CU_TRY(pack(dst, (long long)canonPitch, d0, step, stride < 0 ? -(long long)rawPitch : (long long)rawPitch));
     } else {
         const size_t bytes = (size_t)(hi - lo) + 1;
         if ((rc = rawBuf.ensure(bytes))) return rc;
         CU_TRY(cudaMemcpyAsync(rawBuf.ptr, img + lo, bytes, cudaMemcpyHostToDevice, s));
-        CU_TRY(ssimk::launch_pack_u8(s, dst, (long long)canonPitch, (const uint8_t*)rawBuf.ptr - lo, step, stride, (int)W, (int)H));
+        CU_TRY(pack(dst, (long long)canonPitch, (const uint8_t*)rawBuf.ptr - lo, step, stride));
     }
     return 0;
 }
@@ -399,15 +405,15 @@ struct GeneralJob {
 
 int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, uint32_t outRows, const uint8_t* a, ptrdiff_t stepA,
                     ptrdiff_t strideA, const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep,
-                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job)
+                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job, bool luma = false)
 {
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const uint8_t *pa, *pb;
     size_t pitchA, pitchB;
     int rc;
-    if ((rc = canonical_plane(c, s, a, stepA, strideA, W, srcRows, c->planeA, c->rawA, &pa, &pitchA))) return rc;
-    if ((rc = canonical_plane(c, s, b, stepB, strideB, W, srcRows, c->planeB, c->rawB, &pb, &pitchB))) return rc;
+    if ((rc = canonical_plane(c, s, a, stepA, strideA, W, srcRows, c->planeA, c->rawA, &pa, &pitchA, luma))) return rc;
+    if ((rc = canonical_plane(c, s, b, stepB, strideB, W, srcRows, c->planeB, c->rawB, &pb, &pitchB, luma))) return rc;
 
     // map destination: write straight into a canonical device map of the caller, else into scratch
     float* dMap = nullptr;
@@ -716,6 +722,26 @@ int ssim_cuda_compute(int device, uint32_t width, uint32_t height, const uint8_t
     int rc = get_context(device, &c);
     if (rc) return rc;
     return compute_general(c, width, height, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim);
+}
+
+int ssim_cuda_compute_luma(int device, uint32_t width, uint32_t height, const uint8_t* rgbA, ptrdiff_t stepA, ptrdiff_t strideA,
+                           const uint8_t* rgbB, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
+{
+    if (ssim == nullptr && map == nullptr) return fail(EINVAL, "both ssim and map are NULL, nothing would be computed");
+    if (rgbA == nullptr || rgbB == nullptr) return fail(EINVAL, "image pointer is NULL");
+    if (width == 0 || height == 0) return fail(EINVAL, "width and height must be non-zero");
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    GeneralJob job;
+    rc = enqueue_general(c, width, height, 0, height, rgbA, stepA, strideA, rgbB, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job, true);
+    if (rc) return rc;
+    float hostSsim = 0.f;
+    if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = finish_general(job))) return rc;
+    if (ssim) *ssim = hostSsim;
+    return 0;
 }
 
 int ssim_cuda_compute_device(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,

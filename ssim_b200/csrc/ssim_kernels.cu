@@ -475,6 +475,20 @@ __global__ void pack_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, co
     if (x < width && y < height) dst[(long long)y * dstPitch + x] = src[(long long)x * step + (long long)y * stride];
 }
 
+// BT.601 luma of an interleaved RGB(A) image, integer arithmetic identical to the reference CLI's CPU loop
+// (src/ssim-cli.cpp:158-186: (19595 R + 38470 G + 7471 B + 32768) >> 16), written as a dense pitched plane.
+__global__ void pack_luma_kernel(uint8_t* __restrict__ dst, long long dstPitch, const uint8_t* __restrict__ src,
+                                 long long step, long long stride, int width, int height)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < width && y < height) {
+        const uint8_t* px = src + (long long)x * step + (long long)y * stride;
+        const unsigned r = px[0], g = px[1], b = px[2];
+        dst[(long long)y * dstPitch + x] = (uint8_t)((r * 19595u + g * 38470u + b * 7471u + 32768u) >> 16);
+    }
+}
+
 // scatters a dense float map into an arbitrarily strided one (ssimStep != 1, negative ssimStride; src/ssim.cpp:661-667)
 __global__ void scatter_map_kernel(float* __restrict__ dst, long long dstStep, long long dstStride,
                                    const float* __restrict__ src, long long srcPitch, int width, int height)
@@ -544,6 +558,14 @@ cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch
 {
     const dim3 block(64, 4);
     pack_u8_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, step, stride, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_luma(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
+                             long long step, long long stride, int width, int height)
+{
+    const dim3 block(64, 4);
+    pack_luma_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, step, stride, width, height);
     return cudaGetLastError();
 }
 
