@@ -70,6 +70,17 @@ int ssim_cuda_compute_luma(int device, uint32_t width, uint32_t height,
                            float* ssim);
 
 /*
+ * All channels of two interleaved host images in one pass: channel c of pixel (x,y) is a[y*strideA + x*channels + c].
+ * Replaces the per-channel loop of the reference's CLI and tests (src/ssim-cli.cpp:199-209, tests/rmgr-ssim-tests.cpp:273-291),
+ * which call compute_ssim() once per channel with step = channels on the same bytes: here the bytes are uploaded once, split
+ * on the GPU and all channels go through ONE fused launch.  ssim (or NULL) receives `channels` floats; map (or NULL)
+ * receives channels floats per pixel: map[y*mapStride + x*channels + c].  Strides must be positive.  Blocking.
+ */
+int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint32_t channels,
+                               const uint8_t* a, ptrdiff_t strideA, const uint8_t* b, ptrdiff_t strideB,
+                               float* map, ptrdiff_t mapStride, float* ssim);
+
+/*
  * Device-resident planes, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
  * stream).  `frames` independent pairs are processed by ONE kernel launch (+ one small reduction launch).
  *

@@ -46,6 +46,9 @@ def cuda_lib():
     lib.ssim_cuda_compute.restype = C.c_int
     lib.ssim_cuda_compute_luma.argtypes = lib.ssim_cuda_compute.argtypes
     lib.ssim_cuda_compute_luma.restype = C.c_int
+    lib.ssim_cuda_compute_channels.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.c_ssize_t, u8p, C.c_ssize_t,
+                                               f32p, C.c_ssize_t, C.POINTER(C.c_float)]
+    lib.ssim_cuda_compute_channels.restype = C.c_int
     lib.ssim_cuda_compute_device.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                              u8p, C.c_size_t, C.c_size_t, u8p, C.c_size_t, C.c_size_t,
                                              f32p, C.c_size_t, C.c_size_t, f64p, f32p]
@@ -125,6 +128,16 @@ def compute_strips(devices, a, b, want_map=False):
     _check(cuda_lib().ssim_cuda_compute_strips(len(devices), devs, w, h, a.ctypes.data, 1, w, b.ctypes.data, 1, w,
                                               m.ctypes.data if want_map else None, 1, w, C.byref(out)))
     return np.float32(out.value), m
+
+
+def compute_channels(a, b, want_map=False, device=0):
+    """ssim_cuda_compute_channels() on interleaved uint8 arrays of shape (H, W, C); returns (ssim[C], map (H, W, C) or None)."""
+    h, w, c = a.shape
+    m = np.empty((h, w, c), dtype=np.float32) if want_map else None
+    out = (C.c_float * c)()
+    _check(cuda_lib().ssim_cuda_compute_channels(device, w, h, c, a.ctypes.data, w * c, b.ctypes.data, w * c,
+                                                m.ctypes.data if want_map else None, w * c, out))
+    return np.array(out, dtype=np.float32), m
 
 
 def synth_fill(device, stream, d_a, pitch_a, d_b, pitch_b, width, rows, y0=0, frame=0, seed=0x5517):

@@ -344,13 +344,15 @@ int main(int argc, char* argv[])
         if (rc != 0) return report(rc);
         printf("% 7.4f\n", ssim);
     } else {
-        float average = 0.0f;
+        // every channel (src/ssim-cli.cpp:199-209 loops compute_ssim over the channels; here one pass does them all)
+        float ssims[16], average = 0.0f;
+        const char* env = getenv("SSIM_CUDA_DEVICE");
+        const int32_t rc = ssim_cuda_compute_channels(env ? atoi(env) : 0, (uint32_t)W, (uint32_t)H, (uint32_t)C, img1.pixels.data(), (ptrdiff_t)W * C,
+                                                      img2.pixels.data(), (ptrdiff_t)W * C, mapPtr, (ptrdiff_t)W * C, ssims);
+        if (rc != 0) return report(rc);
         for (int c = 0; c < C; ++c) {
-            float ssim;
-            const int32_t rc = compute_channel(&ssim, img1, img2, c, mapPtr, mapChannels, mapPtr ? c : 0);
-            if (rc != 0) return report(rc);
-            printf("Channel %u: % 7.4f\n", c, ssim);
-            average += ssim;
+            printf("Channel %u: % 7.4f\n", c, ssims[c]);
+            average += ssims[c];
         }
         printf("Average  : % 7.4f\n", average / C);
     }

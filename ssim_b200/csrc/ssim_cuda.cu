@@ -744,6 +744,54 @@ int ssim_cuda_compute_luma(int device, uint32_t width, uint32_t height, const ui
     return 0;
 }
 
+int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint32_t channels, const uint8_t* a, ptrdiff_t strideA,
+                               const uint8_t* b, ptrdiff_t strideB, float* map, ptrdiff_t mapStride, float* ssim)
+{
+    if (ssim == nullptr && map == nullptr) return fail(EINVAL, "both ssim and map are NULL, nothing would be computed");
+    if (a == nullptr || b == nullptr) return fail(EINVAL, "image pointer is NULL");
+    if (width == 0 || height == 0 || channels == 0 || channels > 16) return fail(EINVAL, "bad dimensions / channel count");
+    const size_t rowBytes = (size_t)width * channels;
+    if (strideA < (ptrdiff_t)rowBytes || strideB < (ptrdiff_t)rowBytes || (map && mapStride < (ptrdiff_t)rowBytes))
+        return fail(EINVAL, "strides must be positive and cover width*channels");
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    CU_TRY(cudaSetDevice(device));
+    cudaStream_t s = c->stream;
+    const size_t rawPitch = align_up(rowBytes, 16), pitch = align_up(width, 16), plane = pitch * height;
+    const size_t mapPitch = align_up(width, 4), mapPlane = mapPitch * height;
+    if ((rc = c->rawA.ensure(rawPitch * height)) || (rc = c->rawB.ensure(rawPitch * height))) return rc;
+    if ((rc = c->planeA.ensure(plane * channels)) || (rc = c->planeB.ensure(plane * channels))) return rc;
+    if ((rc = c->scalars.ensure((sizeof(double) + sizeof(float)) * 16))) return rc;
+    float* dMaps = nullptr;
+    float* dInter = nullptr;
+    if (map) {
+        if ((rc = c->map.ensure((mapPlane * channels + rowBytes * height) * sizeof(float)))) return rc;
+        dMaps = (float*)c->map.ptr;
+        dInter = dMaps + mapPlane * channels;
+    }
+    // one upload of the interleaved bytes, one split into planes, ONE fused launch with the channels as frames
+    CU_TRY(cudaMemcpy2DAsync(c->rawA.ptr, rawPitch, a, (size_t)strideA, rowBytes, height, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpy2DAsync(c->rawB.ptr, rawPitch, b, (size_t)strideB, rowBytes, height, cudaMemcpyHostToDevice, s));
+    CU_TRY(ssimk::launch_deinterleave_u8(s, (uint8_t*)c->planeA.ptr, (long long)pitch, (long long)plane, (const uint8_t*)c->rawA.ptr, (long long)rawPitch, (int)channels, (int)width, (int)height));
+    CU_TRY(ssimk::launch_deinterleave_u8(s, (uint8_t*)c->planeB.ptr, (long long)pitch, (long long)plane, (const uint8_t*)c->rawB.ptr, (long long)rawPitch, (int)channels, (int)width, (int)height));
+    double* dSums = (double*)c->scalars.ptr;
+    float* dSsim = (float*)((char*)c->scalars.ptr + sizeof(double) * 16);
+    rc = compute_device_impl(c, s, width, height, 0, height, channels, (const uint8_t*)c->planeA.ptr, pitch, plane, (const uint8_t*)c->planeB.ptr, pitch, plane,
+                             dMaps, mapPitch, mapPlane, dSums, dSsim);
+    if (rc) return rc;
+    float hostSsim[16];
+    if (ssim) CU_TRY(cudaMemcpyAsync(hostSsim, dSsim, sizeof(float) * channels, cudaMemcpyDeviceToHost, s));
+    if (map) {
+        CU_TRY(ssimk::launch_interleave_map(s, dInter, (long long)rowBytes, dMaps, (long long)mapPitch, (long long)mapPlane, (int)channels, (int)width, (int)height));
+        CU_TRY(cudaMemcpy2DAsync(map, (size_t)mapStride * sizeof(float), dInter, rowBytes * sizeof(float), rowBytes * sizeof(float), height, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (ssim) memcpy(ssim, hostSsim, sizeof(float) * channels);
+    return 0;
+}
+
 int ssim_cuda_compute_device(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,
                              const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB, size_t frameStrideB,
                              float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim)

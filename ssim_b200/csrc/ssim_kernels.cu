@@ -489,6 +489,28 @@ __global__ void pack_luma_kernel(uint8_t* __restrict__ dst, long long dstPitch, 
     }
 }
 
+// splits an interleaved C-channel image into C dense pitched planes (plane c at dst + c*planeStride) in one read of the bytes
+__global__ void deinterleave_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, long long planeStride,
+                                       const uint8_t* __restrict__ src, long long srcPitch, int channels, int width, int height)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < width && y < height) {
+        const uint8_t* px = src + (long long)y * srcPitch + (long long)x * channels;
+        for (int c = 0; c < channels; ++c) dst[c * planeStride + (long long)y * dstPitch + x] = px[c];
+    }
+}
+
+// merges C dense float maps (map c at src + c*planeStride) into one interleaved map: dst[y*dstPitch + x*C + c]
+__global__ void interleave_map_kernel(float* __restrict__ dst, long long dstPitch, const float* __restrict__ src, long long srcPitch,
+                                      long long planeStride, int channels, int width, int height)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < width && y < height)
+        for (int c = 0; c < channels; ++c) dst[(long long)y * dstPitch + (long long)x * channels + c] = src[c * planeStride + (long long)y * srcPitch + x];
+}
+
 // scatters a dense float map into an arbitrarily strided one (ssimStep != 1, negative ssimStride; src/ssim.cpp:661-667)
 __global__ void scatter_map_kernel(float* __restrict__ dst, long long dstStep, long long dstStride,
                                    const float* __restrict__ src, long long srcPitch, int width, int height)
@@ -566,6 +588,22 @@ cudaError_t launch_pack_luma(cudaStream_t stream, uint8_t* dst, long long dstPit
 {
     const dim3 block(64, 4);
     pack_luma_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, step, stride, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deinterleave_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, long long planeStride, const uint8_t* src,
+                                   long long srcPitch, int channels, int width, int height)
+{
+    const dim3 block(64, 4);
+    deinterleave_u8_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, channels, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_interleave_map(cudaStream_t stream, float* dst, long long dstPitch, const float* src, long long srcPitch,
+                                  long long planeStride, int channels, int width, int height)
+{
+    const dim3 block(64, 4);
+    interleave_map_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, srcPitch, planeStride, channels, width, height);
     return cudaGetLastError();
 }
 

@@ -70,6 +70,10 @@ cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch
                            long long step, long long stride, int width, int height);
 cudaError_t launch_pack_luma(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
                              long long step, long long stride, int width, int height);
+cudaError_t launch_deinterleave_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, long long planeStride, const uint8_t* src,
+                                   long long srcPitch, int channels, int width, int height);
+cudaError_t launch_interleave_map(cudaStream_t stream, float* dst, long long dstPitch, const float* src, long long srcPitch,
+                                  long long planeStride, int channels, int width, int height);
 cudaError_t launch_scatter_map(cudaStream_t stream, float* dst, long long dstStep, long long dstStride,
                                const float* src, long long srcPitch, int width, int height);
 cudaError_t launch_synth_fill(cudaStream_t stream, uint8_t* dA, long long pitchA, uint8_t* dB, long long pitchB,

@@ -106,6 +106,23 @@ def test_device_pointers_through_the_reference_api():
     assert abs(out.value - float(o)) <= GLOBAL_TOL
 
 
+def test_all_channels_in_one_pass(bbb360):
+    """interleaved RGB, all channels from one upload == the per-channel calls (step = 3) == oracle"""
+    a, b = np.ascontiguousarray(bbb360["jpg50"]), np.ascontiguousarray(bbb360["png"])       # (80, 640, 3)
+    s, m = api.compute_channels(a, b, want_map=True)
+    for ch in range(3):
+        o, _, om = oracle.oracle_ssim(a, b, want_map=True, step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, width=640, height=80, a_off=ch, b_off=ch)
+        one, m1 = api.compute_ssim(a, b, want_map=True, width=640, height=80, step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, a_off=ch, b_off=ch)
+        assert abs(float(s[ch]) - float(o)) <= GLOBAL_TOL and np.abs(m[..., ch] - om).max() <= PIXEL_TOL
+        # (same math, different work decomposition => per-item centring pixels differ: equal to rounding, not bitwise)
+        assert abs(float(s[ch]) - float(one)) <= 2e-7 and np.abs(m[..., ch] - m1).max() <= 3e-4
+    s2, _ = api.compute_channels(a, b)
+    assert np.array_equal(s, s2)
+    g = np.ascontiguousarray(a[..., :1])
+    s1, _ = api.compute_channels(g, np.ascontiguousarray(b[..., :1]))
+    assert abs(float(s1[0]) - float(s[0])) <= 2e-7
+
+
 def test_device_argument_errors():
     lib = api.cuda_lib()
     t = torch.zeros(64 * 64, dtype=torch.uint8, device="cuda")
