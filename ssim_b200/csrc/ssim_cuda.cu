@@ -258,14 +258,30 @@ int get_partials(Context* c, cudaStream_t stream, size_t bytes, double** out)
     return 0;
 }
 
+// Chunked callers (the pipelined host path) encode the four tensor maps once, hand every chunk a slice of one partial-sum
+// buffer and run a single finalize at the end: per chunk that leaves exactly one kernel launch.
+struct ChunkPlan {
+    const CUtensorMap* maps = nullptr;      // {A8, A1, B8, B1}, encoded once for the whole plane
+    double* partials = nullptr;             // this chunk's slice
+    long long* itemsOut = nullptr;          // receives the number of partials written
+};
+
+long long plan_items(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames)
+{
+    int segRows, segs;
+    choose_segments(c, width, outRows, frames, &segRows, &segs);
+    return (long long)((width + ssimk::kBandW - 1) / ssimk::kBandW) * segs * frames;
+}
+
 int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
                         uint32_t frames, const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB,
-                        size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim)
+                        size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim,
+                        const ChunkPlan* chunk = nullptr)
 {
     g_lastLaunches = 0;
     if (width == 0 || srcRows == 0 || outRows == 0 || frames == 0) return fail(EINVAL, "width, rows and frames must be non-zero");
     if (dA == nullptr || dB == nullptr) return fail(EINVAL, "dA or dB is NULL");
-    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr) return fail(EINVAL, "no output requested");
+    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr && chunk == nullptr) return fail(EINVAL, "no output requested");
     if ((uint64_t)outY0 + outRows > srcRows) return fail(EINVAL, "output rows [%u,%u) exceed the %u source rows", outY0, outY0 + outRows, srcRows);
     if (width > 0x7fffff00u || srcRows > 0x7fffff00u) return fail(EINVAL, "dimensions too large");
     if (((uintptr_t)dA | (uintptr_t)dB | pitchA | pitchB) & 15) return fail(EINVAL, "plane base addresses and pitches must be multiples of 16 bytes");
@@ -281,14 +297,20 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (itemsPerFrame > 0x7fffffffLL) return fail(EINVAL, "image too large");
 
     double* partials = nullptr;
-    int rc = get_partials(c, stream, (size_t)items * sizeof(double), &partials);
-    if (rc) return rc;
-
-    CUtensorMap tmA8, tmA1, tmB8, tmB1;
-    if ((rc = make_plane_map(&tmA8, dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows))) return rc;
-    if ((rc = make_plane_map(&tmA1, dA, width, srcRows, frames, pitchA, frameStrideA, 1))) return rc;
-    if ((rc = make_plane_map(&tmB8, dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows))) return rc;
-    if ((rc = make_plane_map(&tmB1, dB, width, srcRows, frames, pitchB, frameStrideB, 1))) return rc;
+    int rc = 0;
+    CUtensorMap local[4];
+    const CUtensorMap* tm = local;
+    if (chunk) {
+        partials = chunk->partials;
+        tm = chunk->maps;
+        if (chunk->itemsOut) *chunk->itemsOut = items;
+    } else {
+        if ((rc = get_partials(c, stream, (size_t)items * sizeof(double), &partials))) return rc;
+        if ((rc = make_plane_map(&local[0], dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows))) return rc;
+        if ((rc = make_plane_map(&local[1], dA, width, srcRows, frames, pitchA, frameStrideA, 1))) return rc;
+        if ((rc = make_plane_map(&local[2], dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows))) return rc;
+        if ((rc = make_plane_map(&local[3], dB, width, srcRows, frames, pitchB, frameStrideB, 1))) return rc;
+    }
 
     ssimk::FusedParams p;
     memset(&p, 0, sizeof(p));
@@ -312,10 +334,10 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
         for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];
         p.eps2 = (float)(2.0 * (s1 * s1 - 1.0));
     }
-    CU_TRY(ssimk::launch_fused(stream, tmA8, tmA1, tmB8, tmB1, p));
+    CU_TRY(ssimk::launch_fused(stream, tm[0], tm[1], tm[2], tm[3], p));
     g_lastLaunches = 1;
 
-    if (dSums || dSsim) {
+    if (!chunk && (dSums || dSsim)) {
         ssimk::FinalizeParams f;
         f.partials = partials; f.sums = dSums; f.ssim = dSsim;
         f.itemsPerFrame = (int)itemsPerFrame;
@@ -484,17 +506,35 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
     int rc;
     if ((rc = c->planeA.ensure(pitch * H)) || (rc = c->planeB.ensure(pitch * H))) return rc;
     if (map && (rc = c->map.ensure(mapPitch * H * sizeof(float)))) return rc;
-    const uint32_t targetRows = std::max<uint32_t>(64, (uint32_t)((1u << 20) / std::max<uint32_t>(W, 1)));   // ~1 MB of pixels per chunk and image
-    int nChunks = (int)std::min<uint32_t>(Context::kMaxChunks, (H + targetRows - 1) / targetRows);
-    nChunks = std::max(nChunks, 2);
+    // Uniform chunks of ~2 MB of pixels per image: the per-chunk host API cost (~20 us: three copies, two events, one launch)
+    // makes finer chunks lose, and graded chunk sizes (small first/last chunks to shorten pipeline fill and drain) measured
+    // no better than 4 uniform chunks for a 4K pair (tools/dev/e2e_sweep.py).
+    static const uint32_t chunkBytes = [] { const char* e = getenv("SSIM_CUDA_CHUNK_KB"); return (e ? (uint32_t)atoi(e) : 2048u) << 10; }();
+    const uint32_t targetRows = std::max<uint32_t>(64, chunkBytes / std::max<uint32_t>(W, 1));
+    const int nChunks = std::max<int>(2, (int)std::min<uint32_t>(Context::kMaxChunks, (H + targetRows - 1) / targetRows));
+    std::vector<uint32_t> bounds(nChunks + 1);                 // chunk k covers rows [bounds[k], bounds[k+1])
+    for (int k = 0; k <= nChunks; ++k) bounds[k] = (uint32_t)((uint64_t)H * k / nChunks);
     if ((rc = c->chunkSums.ensure(sizeof(double) * Context::kMaxChunks)) || (rc = c->chunkSumsHost.ensure(sizeof(double) * Context::kMaxChunks))) return rc;
     uint8_t *dA = (uint8_t*)c->planeA.ptr, *dB = (uint8_t*)c->planeB.ptr;
     float* dMap = map ? (float*)c->map.ptr : nullptr;
     double* dSums = (double*)c->chunkSums.ptr;
 
-    uint32_t copied = 0;                                       // rows [0, copied) are on the device (or in flight on streamIn)
+    // tensor maps of the whole planes, encoded once; one partial-sum buffer for all chunks, one finalize at the end
+    CUtensorMap maps[4];
+    if ((rc = make_plane_map(&maps[0], dA, W, H, 1, pitch, 0, ssimk::kLoadRows)) || (rc = make_plane_map(&maps[1], dA, W, H, 1, pitch, 0, 1)) ||
+        (rc = make_plane_map(&maps[2], dB, W, H, 1, pitch, 0, ssimk::kLoadRows)) || (rc = make_plane_map(&maps[3], dB, W, H, 1, pitch, 0, 1))) return rc;
+    long long totalItems = 0;
     for (int k = 0; k < nChunks; ++k) {
-        const uint32_t y0 = (uint32_t)((uint64_t)H * k / nChunks), y1 = (uint32_t)((uint64_t)H * (k + 1) / nChunks);
+        const uint32_t y0 = bounds[k], y1 = bounds[k + 1];
+        if (y1 > y0) totalItems += plan_items(c, W, y1 - y0, 1);
+    }
+    double* partials = nullptr;
+    if ((rc = get_partials(c, c->stream, (size_t)totalItems * sizeof(double), &partials))) return rc;
+
+    uint32_t copied = 0;                                       // rows [0, copied) are on the device (or in flight on streamIn)
+    long long itemsDone = 0;
+    for (int k = 0; k < nChunks; ++k) {
+        const uint32_t y0 = bounds[k], y1 = bounds[k + 1];
         const uint32_t need = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
         if (need > copied) {
             CU_TRY(cudaMemcpy2DAsync(dA + (size_t)copied * pitch, pitch, a + (ptrdiff_t)copied * strideA, (size_t)strideA, W, need - copied,
@@ -503,12 +543,16 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
                                      cudaMemcpyHostToDevice, c->streamIn));
             copied = need;
         }
+        if (y1 == y0) continue;
         CU_TRY(cudaEventRecord(c->evIn[k], c->streamIn));
         CU_TRY(cudaStreamWaitEvent(c->stream, c->evIn[k], 0));
-        if (y1 == y0) { CU_TRY(cudaMemsetAsync(dSums + k, 0, sizeof(double), c->stream)); continue; }
+        ChunkPlan plan;
+        long long items = 0;
+        plan.maps = maps; plan.partials = partials + itemsDone; plan.itemsOut = &items;
         rc = compute_device_impl(c, c->stream, W, H, y0, y1 - y0, 1, dA, pitch, 0, dB, pitch, 0,
-                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, dSums + k, nullptr);
+                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, nullptr, nullptr, &plan);
         if (rc) return rc;
+        itemsDone += items;
         if (map) {
             CU_TRY(cudaEventRecord(c->evDone[k], c->stream));
             CU_TRY(cudaStreamWaitEvent(c->streamOut, c->evDone[k], 0));
@@ -516,14 +560,14 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
                                      mapPitch * sizeof(float), (size_t)W * sizeof(float), y1 - y0, cudaMemcpyDeviceToHost, c->streamOut));
         }
     }
-    CU_TRY(cudaMemcpyAsync(c->chunkSumsHost.ptr, dSums, sizeof(double) * nChunks, cudaMemcpyDeviceToHost, c->stream));
+    // all chunks' partials in one fixed-order reduction (deterministic), then the reference's last step (src/ssim.cpp:1102)
+    ssimk::FinalizeParams f;
+    f.partials = partials; f.sums = dSums; f.ssim = nullptr; f.itemsPerFrame = (int)itemsDone; f.invCount = 0.0;
+    CU_TRY(ssimk::launch_finalize(c->stream, f, 1));
+    CU_TRY(cudaMemcpyAsync(c->chunkSumsHost.ptr, dSums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (map) CU_TRY(cudaStreamSynchronize(c->streamOut));
-    if (ssim) {
-        double total = 0.0;                                    // fixed order: deterministic
-        for (int k = 0; k < nChunks; ++k) total += ((const double*)c->chunkSumsHost.ptr)[k];
-        *ssim = (float)(total / (double)(uint32_t)(W * H));    // src/ssim.cpp:1102
-    }
+    if (ssim) *ssim = (float)(((const double*)c->chunkSumsHost.ptr)[0] / (double)(uint32_t)(W * H));
     return 0;
 }
 
