@@ -133,3 +133,43 @@ def test_device_argument_errors():
     assert f(0, None, 60, 64, 0, 64, 1, t.data_ptr(), 60, 0, t.data_ptr(), 60, 0, None, 0, 0, s.data_ptr(), None) == 22  # pitch % 16
     assert f(0, None, 64, 64, 0, 64, 1, t.data_ptr() + 4, 64, 0, t.data_ptr(), 64, 0, None, 0, 0, s.data_ptr(), None) == 22  # base % 16
     assert f(99, None, 64, 64, 0, 64, 1, t.data_ptr(), 64, 0, t.data_ptr(), 64, 0, None, 0, 0, s.data_ptr(), None) == 22  # bad device
+
+
+def test_concurrent_calls_from_many_threads():
+    """the reference is re-entrant (SURVEY 8b 'Threading'); the GPU path serialises per device internally"""
+    import threading
+    pairs = [synth_pair(300 + 17 * i, 120 + 5 * i, i) for i in range(6)]
+    want = [oracle.oracle_ssim(a, b, want_map=True) for a, b in pairs]
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(5):
+                a, b = pairs[k]
+                s, m = api.compute_ssim(a, b, want_map=True)
+                if abs(float(s) - float(want[k][0])) > GLOBAL_TOL or np.abs(m - want[k][2]).max() > PIXEL_TOL:
+                    errors.append((k, float(s), float(want[k][0])))
+        except Exception as e:            # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    # two streams on the device API at the same time (separate partial-sum workspaces per stream)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for st, (a, b) in zip((s1, s2), pairs[:2]):
+        h, w = a.shape
+        pw = (w + 15) // 16 * 16
+        da = torch.zeros((h, pw), dtype=torch.uint8, device="cuda"); db = torch.zeros_like(da)
+        da[:, :w] = _dev(a); db[:, :w] = _dev(b)
+        ds = torch.empty(1, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        api.compute_device(0, st.cuda_stream, w, h, 0, h, 1, da.data_ptr(), pw, 0, db.data_ptr(), pw, 0, None, 0, 0, None, ds.data_ptr())
+        outs.append((ds, da, db))
+    torch.cuda.synchronize()
+    for (ds, _, _), wv in zip(outs, want[:2]):
+        assert abs(float(ds.item()) - float(wv[0])) <= GLOBAL_TOL
