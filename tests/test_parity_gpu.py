@@ -178,6 +178,57 @@ def test_flat_and_extreme_images():
     _check_pair("independent noise", a, b)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_layouts_against_oracle(seed):
+    """fuzz of the general layout path: random size, per-image step/stride (interleaved, padded, bottom-up, right-to-left,
+    column-major) and map step/stride; the oracle walks the same addresses (reference ssim.h:481-499 addressing)"""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(1, 150)), int(rng.integers(1, 90))
+
+    def layout(buf_rng):
+        kind = buf_rng.integers(0, 5)
+        step = int(buf_rng.integers(1, 5))
+        pad = int(buf_rng.integers(0, 9))
+        if kind == 4:                                    # column-major: step spans a column
+            step_b, stride_b = h * step + pad, step
+            size = (w - 1) * step_b + (h - 1) * stride_b + 1
+            off = 0
+        else:
+            row = w * step + pad
+            step_b, stride_b, off = step, row, int(buf_rng.integers(0, step))
+            size = h * row + step
+            if kind in (1, 3):                           # bottom-up
+                off += (h - 1) * row
+                stride_b = -row
+            if kind in (2, 3):                           # right-to-left
+                off += (w - 1) * step
+                step_b = -step
+        return step_b, stride_b, off, size
+
+    sa, ra, oa, na = layout(rng)
+    sb, rb, ob, nb = layout(rng)
+    a = rng.integers(0, 256, na, dtype=np.uint8)
+    b = rng.integers(0, 256, nb, dtype=np.uint8)
+    # make B a noisy copy of A at the addressed pixels so that SSIM is not ~0
+    ys, xs = np.mgrid[0:h, 0:w]
+    b[ob + xs * sb + ys * rb] = np.clip(a[oa + xs * sa + ys * ra].astype(int) + rng.integers(-12, 13, (h, w)), 0, 255).astype(np.uint8)
+    ms = int(rng.integers(1, 4))
+    mrow = w * ms + int(rng.integers(0, 5))
+    flip = bool(rng.integers(0, 2))
+    mbuf = np.full(h * mrow + ms, -5.0, np.float32)
+    s, _ = api.compute_ssim(a, b, width=w, height=h, step_a=sa, stride_a=ra, a_off=oa, step_b=sb, stride_b=rb, b_off=ob,
+                            ssim_map=mbuf, map_step=ms, map_stride=-mrow if flip else mrow, map_off=(h - 1) * mrow if flip else 0)
+    o, _, om = oracle.oracle_ssim(a, b, want_map=True, width=w, height=h, step_a=sa, stride_a=ra, a_off=oa, step_b=sb, stride_b=rb, b_off=ob)
+    assert abs(float(s) - float(o)) <= GLOBAL_TOL
+    got = mbuf[:h * mrow].reshape(h, mrow)[:, 0:w * ms:ms]
+    got = got[::-1] if flip else got
+    assert np.abs(got - om).max() <= PIXEL_TOL
+    touched = np.zeros(mbuf.size, bool)
+    idx = ((h - 1 - ys) if flip else ys) * mrow + xs * ms
+    touched[idx] = True
+    assert (mbuf[~touched] == -5.0).all()                # nothing outside the addressed floats is written
+
+
 def test_determinism():
     a, b = synth_pair(1000, 700, 9)
     s1, m1 = api.compute_ssim(a, b, want_map=True)
