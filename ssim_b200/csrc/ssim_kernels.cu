@@ -231,13 +231,19 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
         }
 
         // Ring position of this lane's row: input row i = 8*blk + hr lives in half (i / 11) & 1 at row t = i % 11.
-        // Layout of a ring row: two planes of 64 packed pairs, {E_h[a'], E_h[b']} at +0 and {E_h[(a'-b')^2], E_h[a'b']} at
-        // +512; column c sits at 8*(c ^ ((c>>4) | ((t&3)<<2))).  The XOR makes both these 8-byte stores (lanes = 4 rows x
-        // 4 column groups per half-warp) and the consumer's 8-byte loads (16 adjacent columns per half-warp) conflict free.
+        // Layout of a ring row (1056 bytes): two planes of 64 packed pairs, {E_h[a'], E_h[b']} at +0 and
+        // {E_h[(a'-b')^2], E_h[a'b']} at +512, then 32 bytes of padding; column c sits at 8*(c ^ (c>>4)).
+        // Bank-conflict freedom without any per-access arithmetic: in the producer's 8-byte stores a half-warp is 4 rows x
+        // 4 column groups writing the same j -- the XOR by the group index spreads the groups over 4 adjacent slots and the
+        // 32-byte pad moves each following row by 4 slots (16 distinct slots); in the consumer's 8-byte loads a half-warp
+        // reads 16 adjacent columns of one group (XOR by a constant).  Both sides address "register + immediate": the
+        // store to column j goes to dst[j & 3] + 32*(j >> 2), the load of row t comes from base + 1056*t.
         const int i  = blk * kBlkRows + hr;
         const int ih = i / kTaps, t = i - ih * kTaps;
-        const uint32_t hSwz    = (uint32_t)(hq | ((t & 3) << 2)) << 3;
-        const uint32_t dstBase = ringBase + (uint32_t)((ih & 1) * kTaps + t) * kRingRowBytes + hq * 128;
+        const uint32_t dstRow = ringBase + (uint32_t)((ih & 1) * kTaps + t) * kRingRowBytes + hq * 128;
+        uint32_t dst4[4];
+        #pragma unroll
+        for (int m = 0; m < 4; ++m) dst4[m] = dstRow + ((uint32_t)(m ^ hq) << 3);
 
         u64 hab[16], hsp[16];
         #pragma unroll
@@ -271,7 +277,7 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
             }
             if (ii >= 10) {                                         // output j = ii-10 is complete
                 const int j = ii - 10;
-                const uint32_t dst = dstBase + ((uint32_t)(j << 3) ^ hSwz);
+                const uint32_t dst = dst4[j & 3] + 32 * (j >> 2);
                 sts64(dst, hab[j]);
                 sts64(dst + kRingPlaneBytes, hsp[j]);
             }
@@ -298,9 +304,9 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
     #define TAP(m) w2[(m) < 5 ? 5 - (m) : (m) - 5]
     constexpr float c1 = 6.5025f, c2 = 58.5225f;          // (0.01*255)^2, (0.03*255)^2 as float: src/ssim.cpp:956-960
 
-    // this lane owns columns bx+lane and bx+32+lane (ring layout: see producer_warp)
-    const uint32_t vBase0 = (uint32_t)(lane ^ (lane >> 4)) << 3;
-    const uint32_t vBase1 = (uint32_t)((32 + lane) ^ (2 + (lane >> 4))) << 3;
+    // this lane owns columns bx+lane and bx+32+lane (ring layout: see producer_warp); column c sits at 8*(c ^ (c>>4))
+    const uint32_t vBase0 = ringBase + ((uint32_t)(lane ^ (lane >> 4)) << 3);
+    const uint32_t vBase1 = ringBase + ((uint32_t)((32 + lane) ^ (2 + (lane >> 4))) << 3);
     const bool colOk0 = it.bx + lane < p.width;
     const bool colOk1 = it.bx + 32 + lane < p.width;
 
@@ -321,16 +327,15 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
 
     #pragma unroll 1
     for (int body = 0; body < it.nBodies; ++body) {
-        const uint32_t halfBase = ringBase + (uint32_t)(body & 1) * (kTaps * kRingRowBytes);
+        const uint32_t halfOff = (uint32_t)(body & 1) * (kTaps * kRingRowBytes);
+        const uint32_t col0 = vBase0 + halfOff, col1 = vBase1 + halfOff;
         mbar_wait_sleep(barFull + 8 * (body & 1), (uint32_t)(body >> 1) & 1u, p.backoffNs);
         const int iBase = body * kTaps;
         float bodySum = 0.f;
         #pragma unroll
         for (int t = 0; t < kTaps; ++t) {
-            const uint32_t rowB = halfBase + t * kRingRowBytes;
-            const uint32_t sw   = (uint32_t)(t & 3) << 5;
-            const u64 hab0 = lds64(rowB + (vBase0 ^ sw)), hsp0 = lds64(rowB + (vBase0 ^ sw) + kRingPlaneBytes);
-            const u64 hab1 = lds64(rowB + (vBase1 ^ sw)), hsp1 = lds64(rowB + (vBase1 ^ sw) + kRingPlaneBytes);
+            const u64 hab0 = lds64(col0 + t * kRingRowBytes), hsp0 = lds64(col0 + t * kRingRowBytes + kRingPlaneBytes);
+            const u64 hab1 = lds64(col1 + t * kRingRowBytes), hsp1 = lds64(col1 + t * kRingRowBytes + kRingPlaneBytes);
             #pragma unroll
             for (int s = 0; s < kTaps; ++s) {
                 const int k = (t - s + kTaps) % kTaps;
@@ -406,7 +411,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
                   const __grid_constant__ FusedParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[kPairsPerCta][8];            // per pair: tmaFull[3], (pad), ringFull[2], ringEmpty[2]
+    __shared__ __align__(8) uint64_t bars[kPairsPerCta][8];            // per pair: tmaFull[kStages], (pad), ringFull[2], ringEmpty[2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;

@@ -18,7 +18,7 @@ constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row
                                    // a multiple of 16 bytes -- measured on B200: x = -16 works, x = -8 raises "illegal instruction"
                                    // (tools/dev/tma_probe.cu)
 constexpr int kLoadRows    = 8;    // rows per TMA box (= one horizontal-pass block)
-constexpr int kStages      = 3;    // TMA ring depth per work item
+constexpr int kStages      = 2;    // TMA ring depth per work item (the producer has slack; 3 stages would not fit 2 CTAs/SM)
 constexpr int kPairsPerCta = 4;    // work items per CTA: each is served by one producer warp and one consumer warp
 constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 256: warps 0-3 producers (TMA + horizontal pass), 4-7 consumers
 constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
@@ -27,12 +27,13 @@ constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partn
 constexpr int kImgStageBytes = kBoxW * kLoadRows;        // 1024
 constexpr int kStageBytes    = 2 * kImgStageBytes;       // 2048 (A then B)
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
-constexpr int kRingRowBytes   = 2 * kRingPlaneBytes;     // 1024: {E[a'], E[b']} plane then {E[(a'-b')^2], E[a'b']} plane
+constexpr int kRingRowPad     = 32;                      // consecutive rows start 8 banks apart: see the ring layout in the kernel
+constexpr int kRingRowBytes   = 2 * kRingPlaneBytes + kRingRowPad;   // 1056: {E[a'], E[b']} plane, {E[(a'-b')^2], E[a'b']} plane, pad
 constexpr int kTaps           = 11;
 constexpr int kRingRows       = 2 * kTaps;               // 22: two halves of 11 rows; the consumer's unrolled body is 11 rows
-constexpr int kRingBytes      = kRingRows * kRingRowBytes; // 22528
-constexpr int kPairSmemBytes = kStages * kStageBytes + kRingBytes;  // 28672
-constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;       // 114688 -> 2 CTAs (16 warps) per SM
+constexpr int kRingBytes      = kRingRows * kRingRowBytes; // 23232
+constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;  // 27392
+constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;       // 109568 -> 2 CTAs (16 warps) per SM
 
 struct FusedParams {
     const uint8_t* a;        // raw planes (used only to fetch the per-item centring pixel)
