@@ -282,11 +282,9 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
                 sts64(dst + kRingPlaneBytes, hsp[j]);
             }
         }
-        __syncwarp();                                               // all 32 lanes' stores precede the (releasing) arrives
+        // every lane arrives (barrier count 32): each lane's release covers its own stores, no reliance on warp-level cumulativity
         const int complete = (blk * kBlkRows + kBlkRows) / kTaps;   // ring halves fully written so far
-        if (lane == 0) {
-            for (int hdone = released; hdone < complete; ++hdone) mbar_arrive(barFull + 8 * (hdone & 1));
-        }
+        for (int hdone = released; hdone < complete; ++hdone) mbar_arrive(barFull + 8 * (hdone & 1));
         released = max(released, complete);
     }
     #undef TAP
@@ -347,10 +345,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
                     qab1[s] = fma2(hab1, TAP(k), qab1[s]); qsp1[s] = fma2(hsp1, TAP(k), qsp1[s]);
                 }
             }
-            if (t == kTaps - 1) {                                       // the ring half has been read completely
-                __syncwarp();
-                if (lane == 0) mbar_arrive(barEmpty + 8 * (body & 1));
-            }
+            if (t == kTaps - 1) mbar_arrive(barEmpty + 8 * (body & 1));   // this lane is done reading the half (count 32)
 
             // Output row completed by this input row.  The formula is evaluated unconditionally (the first 10 rows of a
             // segment and the filler rows at its end only cost the pipeline fill); the store and the sum are predicated.
@@ -419,7 +414,8 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     const bool isConsumer = warp >= kPairsPerCta;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kPairsPerCta * 8; ++i) mbar_init(smem_u32(&bars[0][0]) + 8 * i, 1);
+        for (int pr = 0; pr < kPairsPerCta; ++pr)
+            for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[pr][i]), i < 4 ? 1 : 32);   // TMA barriers: 1 arrival; ring full/empty: all 32 lanes
         fence_mbar_init();
         fence_proxy_async();
     }
