@@ -408,7 +408,9 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kPairsPerCta][8];            // per pair: tmaFull[kStages], (pad), ringFull[2], ringEmpty[2]
 
-    const int warp = threadIdx.x >> 5;
+    // shuffled from lane 0 so that the compiler knows the warp index (and everything derived from it: item, smem and
+    // barrier addresses, TMA coordinates) is warp-uniform and keeps it on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int pair = warp & (kPairsPerCta - 1);
     const bool isConsumer = warp >= kPairsPerCta;
@@ -422,8 +424,8 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     __syncthreads();                                                    // the only CTA-wide barrier
 
     const long long item = (long long)blockIdx.x * kPairsPerCta + pair;
-    const uint32_t pairSmem = smem_u32(smem) + pair * kPairSmemBytes;
-    const uint32_t barBase  = smem_u32(&bars[pair][0]);
+    const uint32_t pairSmem = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + pair * kPairSmemBytes;
+    const uint32_t barBase  = __shfl_sync(0xffffffffu, smem_u32(&bars[0][0]), 0) + pair * 64;
 
     // Register hand-over between the two warpgroups: every warp of a warpgroup must execute its setmaxnreg (so it comes
     // before the early exit), and each role's code must follow its own setmaxnreg within the same branch -- ptxas budgets
