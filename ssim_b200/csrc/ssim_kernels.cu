@@ -47,6 +47,11 @@ __device__ __forceinline__ void sts64(uint32_t addr, u64 v) {
     asm volatile("st.shared.u64 [%0], %1;" :: "r"(addr), "l"(v) : "memory");
 }
 
+template <int kOff>
+__device__ __forceinline__ void stg_f32(unsigned long long addr, float v) {
+    asm volatile("st.global.f32 [%0+%1], %2;" :: "l"(addr), "n"(kOff), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
@@ -315,10 +320,13 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
     #pragma unroll
     for (int m = 0; m < kTaps; ++m) qab0[m] = qsp0[m] = qab1[m] = qsp1[m] = 0ull;
 
-    // running map pointer: row of the output completed by the current input row (starts 10 rows above the segment;
-    // never dereferenced there)
-    float* mapPtr = nullptr;
-    if (kMap) mapPtr = p.map + (long long)it.frame * p.mapFrameStride + (long long)(it.oy0 - p.outY0 - 2 * kHalo) * p.mapPitch + it.bx + lane;
+    // Map addressing: one 64-bit per-lane address that advances by the pitch per input row (starts 10 rows above the
+    // segment, never dereferenced there); the second column is an immediate offset.  Stores are written in PTX so
+    // that the address arithmetic stays these two adds per row.
+    unsigned long long mapAddr = 0;
+    const unsigned long long mapPitchBytes = (unsigned long long)p.mapPitch * sizeof(float);
+    if (kMap) mapAddr = (unsigned long long)(p.map + (long long)it.frame * p.mapFrameStride + (long long)(it.oy0 - p.outY0 - 2 * kHalo) * p.mapPitch + it.bx + lane);
+    const bool fullBand = it.bx + kBandW <= p.width;                    // warp-uniform: no column predicates needed
 
     const int nRows = it.nOut + 2 * kHalo;                              // input rows that complete a wanted output
     double total = 0.0;
@@ -329,7 +337,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
         const uint32_t col0 = vBase0 + halfOff, col1 = vBase1 + halfOff;
         mbar_wait_sleep(barFull + 8 * (body & 1), (uint32_t)(body >> 1) & 1u, p.backoffNs);
         const int iBase = body * kTaps;
-        float bodySum = 0.f;
+        float bodySum0 = 0.f, bodySum1 = 0.f;
         #pragma unroll
         for (int t = 0; t < kTaps; ++t) {
             const u64 hab0 = lds64(col0 + t * kRingRowBytes), hsp0 = lds64(col0 + t * kRingRowBytes + kRingPlaneBytes);
@@ -381,14 +389,19 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
                 const float q = num * rc;
                 sv[c] = fmaf(rc, fmaf(-q, den, num), q);
             }
-            const bool ok0 = rowOk && colOk0, ok1 = rowOk && colOk1;
-            if (kMap) {
-                if (ok0) mapPtr[0]  = sv[0];
-                if (ok1) mapPtr[32] = sv[1];
-                mapPtr += p.mapPitch;
+            if (rowOk) {                                                // warp-uniform
+                if (kMap) {
+                    if (fullBand) { stg_f32<0>(mapAddr, sv[0]); stg_f32<128>(mapAddr, sv[1]); }
+                    else {
+                        if (colOk0) stg_f32<0>(mapAddr, sv[0]);
+                        if (colOk1) stg_f32<128>(mapAddr, sv[1]);
+                    }
+                }
+                bodySum0 += sv[0]; bodySum1 += sv[1];
             }
-            bodySum += (ok0 ? sv[0] : 0.f) + (ok1 ? sv[1] : 0.f);
+            if (kMap) mapAddr += mapPitchBytes;
         }
+        const float bodySum = (colOk0 ? bodySum0 : 0.f) + (colOk1 ? bodySum1 : 0.f);
         total += (double)bodySum;                                       // <= 22 values per float partial
     }
     #undef TAP
