@@ -294,7 +294,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     const int bands = (int)((width + ssimk::kBandW - 1) / ssimk::kBandW);
     const long long itemsPerFrame = (long long)bands * segs;
     const long long items = itemsPerFrame * frames;
-    if (itemsPerFrame > 0x7fffffffLL) return fail(EINVAL, "image too large");
+    if (itemsPerFrame > 0x7fffffffLL || items > 0x7fffffffLL) return fail(EINVAL, "image or batch too large");
 
     double* partials = nullptr;
     int rc = 0;
@@ -321,6 +321,8 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.partials = partials;
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.bands = bands; p.segs = segs; p.segRows = segRows; p.items = items;
+    ssimk::fast_div((uint32_t)bands, &p.bandsMul, &p.bandsShift);
+    ssimk::fast_div((uint32_t)segs, &p.segsMul, &p.segsShift);
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];
     p.c1 = (float)((0.01 * 255) * (0.01 * 255));      // src/ssim.cpp:956-960
     p.c2 = (float)((0.03 * 255) * (0.03 * 255));

@@ -124,11 +124,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
 // (frame, segment, band) of a work item, band fastest so that a CTA covers 4 adjacent bands; plus the per-item centring
 // pixels: moments are accumulated on (a - ca), (b - cb), which keeps the fp32 cancellation in E[x^2] - mu^2 small even on
 // flat regions (DESIGN.md "Numerics").  Any integer works; both warps of a pair must of course use the same one.
-__device__ __forceinline__ void decode_item(const FusedParams& p, long long item, ItemCoords& it, float& ca, float& cb)
+__device__ __forceinline__ uint32_t div_u32(uint32_t n, uint32_t mul, uint32_t shift) { return mul ? __umulhi(n, mul) >> shift : n; }
+
+__device__ __forceinline__ void decode_item(const FusedParams& p, uint32_t item, ItemCoords& it, float& ca, float& cb)
 {
-    const int band = (int)(item % p.bands);
-    const int seg  = (int)((item / p.bands) % p.segs);
-    it.frame = (int)(item / ((long long)p.bands * p.segs));
+    const uint32_t q1 = div_u32(item, p.bandsMul, p.bandsShift);       // item / bands          (fast_div() constants)
+    const uint32_t q2 = div_u32(q1, p.segsMul, p.segsShift);           // item / (bands * segs)
+    const int band = (int)(item - q1 * (uint32_t)p.bands);
+    const int seg  = (int)(q1 - q2 * (uint32_t)p.segs);
+    it.frame = (int)q2;
     it.bx    = band * kBandW;                                           // first output column of the band
     it.oy0   = p.outY0 + seg * p.segRows;                               // first output row (plane coordinates)
     it.nOut  = min(p.segRows, p.outY0 + p.outRows - it.oy0);            // output rows of this item
@@ -297,7 +301,7 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
 
 // ---- consumer: vertical pass + formula + outputs
 template <bool kMap>
-__device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCoords& it, int lane, long long item, uint32_t pairSmem,
+__device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCoords& it, int lane, uint32_t item, uint32_t pairSmem,
                                               uint32_t barFull, uint32_t barEmpty, float ca, float cb)
 {
     const uint32_t ringBase = pairSmem + kStages * kStageBytes;
@@ -436,7 +440,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
     }
     __syncthreads();                                                    // the only CTA-wide barrier
 
-    const long long item = (long long)blockIdx.x * kPairsPerCta + pair;
+    const uint32_t item = blockIdx.x * kPairsPerCta + pair;           // < 2^31, checked by the host
     const uint32_t pairSmem = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + pair * kPairSmemBytes;
     const uint32_t barBase  = __shfl_sync(0xffffffffu, smem_u32(&bars[0][0]), 0) + pair * 64;
 

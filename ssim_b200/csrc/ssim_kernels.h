@@ -44,13 +44,26 @@ struct FusedParams {
     double* partials;        // [items] per-warp-item partial sums
     int width, srcRows, outY0, outRows, frames;
     int bands, segs, segRows;
-    long long items;
+    long long items;         // < 2^31 (checked by the host)
+    uint32_t bandsMul, bandsShift, segsMul, segsShift;   // n / d == umulhi(n, mul) >> shift for n < 2^31 (d == 1: mul == 0); see fast_div()
     float g[6];              // separable 11-tap weights: g[d] is the tap at distance d from the centre
     float c1, c2;
     uint32_t magic;          // 0x4B000000 (float 2^23): kept opaque to ptxas, see the kernel
     uint32_t backoffNs;      // sleep between polls of the partner warp's mbarrier
     float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
 };
+
+// Division of item indices by warp-uniform run-time divisors without the 64-bit division subroutine: keeps the whole item
+// decode on the uniform datapath.  mul = ceil(2^(31+L) / d), shift = L - 1, L = ceil(log2 d); exact for n < 2^31.
+inline void fast_div(uint32_t d, uint32_t* mul, uint32_t* shift)
+{
+    if (d <= 1) { *mul = 0; *shift = 0; return; }
+    uint32_t L = 0;
+    while ((1ull << L) < d) ++L;
+    const unsigned long long k = 1ull << (31 + L);
+    *mul = (uint32_t)((k + d - 1) / d);
+    *shift = L - 1;
+}
 
 struct FinalizeParams {
     const double* partials;
