@@ -273,10 +273,10 @@ int get_partials(Context* c, cudaStream_t stream, size_t bytes, double** out)
     return 0;
 }
 
-// Chunked callers (the pipelined host path) encode the four tensor maps once, hand every chunk a slice of one partial-sum
+// Chunked callers (the pipelined host path) encode the two tensor maps once, hand every chunk a slice of one partial-sum
 // buffer and run a single finalize at the end: per chunk that leaves exactly one kernel launch.
 struct ChunkPlan {
-    const CUtensorMap* maps = nullptr;      // {A8, A1, B8, B1}, encoded once for the whole plane
+    const CUtensorMap* maps = nullptr;      // {A, B}, encoded once for the whole plane
     double* partials = nullptr;             // this chunk's slice
     long long* itemsOut = nullptr;          // receives the number of partials written
 };
@@ -313,7 +313,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
 
     double* partials = nullptr;
     int rc = 0;
-    CUtensorMap local[4];
+    CUtensorMap local[2];
     const CUtensorMap* tm = local;
     if (chunk) {
         partials = chunk->partials;
@@ -322,9 +322,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     } else {
         if ((rc = get_partials(c, stream, (size_t)items * sizeof(double), &partials))) return rc;
         if ((rc = make_plane_map(&local[0], dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows))) return rc;
-        if ((rc = make_plane_map(&local[1], dA, width, srcRows, frames, pitchA, frameStrideA, 1))) return rc;
-        if ((rc = make_plane_map(&local[2], dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows))) return rc;
-        if ((rc = make_plane_map(&local[3], dB, width, srcRows, frames, pitchB, frameStrideB, 1))) return rc;
+        if ((rc = make_plane_map(&local[1], dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows))) return rc;
     }
 
     ssimk::FusedParams p;
@@ -351,7 +349,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
         for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];
         p.eps2 = (float)(2.0 * (s1 * s1 - 1.0));
     }
-    CU_TRY(ssimk::launch_fused(stream, tm[0], tm[1], tm[2], tm[3], p));
+    CU_TRY(ssimk::launch_fused(stream, tm[0], tm[1], p));
     g_lastLaunches = 1;
 
     if (!chunk && (dSums || dSsim)) {
@@ -537,9 +535,8 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
     double* dSums = (double*)c->chunkSums.ptr;
 
     // tensor maps of the whole planes, encoded once; one partial-sum buffer for all chunks, one finalize at the end
-    CUtensorMap maps[4];
-    if ((rc = make_plane_map(&maps[0], dA, W, H, 1, pitch, 0, ssimk::kLoadRows)) || (rc = make_plane_map(&maps[1], dA, W, H, 1, pitch, 0, 1)) ||
-        (rc = make_plane_map(&maps[2], dB, W, H, 1, pitch, 0, ssimk::kLoadRows)) || (rc = make_plane_map(&maps[3], dB, W, H, 1, pitch, 0, 1))) return rc;
+    CUtensorMap maps[2];
+    if ((rc = make_plane_map(&maps[0], dA, W, H, 1, pitch, 0, ssimk::kLoadRows)) || (rc = make_plane_map(&maps[1], dB, W, H, 1, pitch, 0, ssimk::kLoadRows))) return rc;
     long long totalItems = 0;
     for (int k = 0; k < nChunks; ++k) {
         const uint32_t y0 = bounds[k], y1 = bounds[k + 1];

@@ -58,17 +58,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" :: "r"(bar), "r"(parity) : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int z, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
@@ -104,9 +93,10 @@ struct ItemCoords {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
-// Waiting on the partner warp: poll once, then back off with an explicit nanosleep between polls.  (try_wait's own
-// suspend-time hint compiles to a NANOSLEEP.SYNCS loop that re-polls almost immediately: 19% of all issued instructions
-// in the first profile of this kernel were that loop.)
+// Waiting on an mbarrier.  Every lane polls (each lane needs its own acquire), but the decision to leave the loop is a
+// warp vote, so the lanes of a warp can never leave a wait in different iterations.  (With warp-uniform barrier
+// addresses ptxas emits no reconvergence point after these loops and turns __syncwarp() into a NOP, so lanes that got
+// apart would stay apart.)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -117,8 +107,13 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!__all_sync(0xffffffffu, mbar_test(bar, parity))) { }
+}
+// Waiting on the partner warp: same, with an explicit nanosleep between polls (try_wait's own suspend-time hint compiles
+// to a NANOSLEEP.SYNCS loop that re-polls almost immediately).
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned backoffNs) {
-    while (!mbar_test(bar, parity)) __nanosleep(backoffNs);
+    while (!__all_sync(0xffffffffu, mbar_test(bar, parity))) __nanosleep(backoffNs);
 }
 
 // (frame, segment, band) of a work item, band fastest so that a CTA covers 4 adjacent bands; plus the per-item centring
@@ -146,34 +141,27 @@ __device__ __forceinline__ void decode_item(const FusedParams& p, uint32_t item,
 }
 
 // ---- producer: TMA + horizontal pass
-__device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUtensorMap* tmA1, const CUtensorMap* tmB8,
-                                              const CUtensorMap* tmB1, const FusedParams& p, const ItemCoords& it, int lane,
+__device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUtensorMap* tmB, const FusedParams& p, const ItemCoords& it, int lane,
                                               uint32_t pairSmem, uint32_t barTma, uint32_t barFull, uint32_t barEmpty, float ca, float cb)
 {
     const uint32_t ringBase = pairSmem + kStages * kStageBytes;
+    const uint32_t barStageEmpty = barTma + 8 * kStages;      // per stage: "all 32 lanes have read it" (count 32)
 
-    // One TMA load = rows [inY0 + 8*blk, +8) x bytes [bx-16, bx+112) of both images.  Rows outside the plane are clamped by
-    // loading single-row boxes at clamped coordinates (replicates the nearest row, src/ssim.cpp:562-582); columns outside
-    // the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
+    // One TMA load = an 8-row box x bytes [bx-16, bx+112) of both images.  A block needs rows [y, y+8) with y = inY0 + 8*blk,
+    // rows outside the plane replicating the nearest one (src/ssim.cpp:562-582): the distinct rows it needs always fit in
+    // the 8-row box starting at clamp(y, 0, srcRows-8), so edge blocks load that box and each lane reads the row
+    // clamp(y + hr) of it.  Columns outside the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
+    const int lastBoxY = max(p.srcRows - kLoadRows, 0);
     auto issue_load = [&](int blk) {
         if (lane == 0) {
             // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes)
             const int stage = blk % kStages;
             const uint32_t bar = barTma + 8 * stage;
             const uint32_t dst = pairSmem + stage * kStageBytes;
-            const int y = it.inY0 + blk * kLoadRows;
+            const int y0 = min(max(it.inY0 + blk * kLoadRows, 0), lastBoxY);
             mbar_arrive_expect_tx(bar, kStageBytes);
-            if (y >= 0 && y + kLoadRows <= p.srcRows) {
-                tma_load_3d(dst, tmA8, it.bx - kBoxLeft, y, it.frame, bar);
-                tma_load_3d(dst + kImgStageBytes, tmB8, it.bx - kBoxLeft, y, it.frame, bar);
-            } else {
-                #pragma unroll 1
-                for (int r = 0; r < kLoadRows; ++r) {
-                    const int yy = min(max(y + r, 0), p.srcRows - 1);
-                    tma_load_3d(dst + r * kBoxW, tmA1, it.bx - kBoxLeft, yy, it.frame, bar);
-                    tma_load_3d(dst + kImgStageBytes + r * kBoxW, tmB1, it.bx - kBoxLeft, yy, it.frame, bar);
-                }
-            }
+            tma_load_3d(dst, tmA, it.bx - kBoxLeft, y0, it.frame, bar);
+            tma_load_3d(dst + kImgStageBytes, tmB, it.bx - kBoxLeft, y0, it.frame, bar);
         }
     };
     #pragma unroll
@@ -225,19 +213,28 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
             __syncwarp();
         }
 
+        // this lane's row of the box: hr, except in edge blocks (warp-uniform test) where rows replicate
+        uint32_t src = stageBase + hSrcOff;
+        {
+            const int y = it.inY0 + blk * kLoadRows;
+            if (y < 0 || y > lastBoxY) {
+                const int y0 = min(max(y, 0), lastBoxY);
+                src = stageBase + (uint32_t)(min(max(y + hr, 0), p.srcRows - 1) - y0) * kBoxW + hq * 16 + (kBoxLeft - 8);
+            }
+        }
         // the window starts 8 bytes into a 16-byte chunk: 8 + 16 + 8 byte loads
-        const uint2 a0 = lds64u(stageBase + hSrcOff), a2 = lds64u(stageBase + hSrcOff + 24);
-        const uint4 a1 = lds128(stageBase + hSrcOff + 8);
-        const uint2 b0 = lds64u(stageBase + kImgStageBytes + hSrcOff), b2 = lds64u(stageBase + kImgStageBytes + hSrcOff + 24);
-        const uint4 b1 = lds128(stageBase + kImgStageBytes + hSrcOff + 8);
+        const uint2 a0 = lds64u(src), a2 = lds64u(src + 24);
+        const uint4 a1 = lds128(src + 8);
+        const uint2 b0 = lds64u(src + kImgStageBytes), b2 = lds64u(src + kImgStageBytes + 24);
+        const uint4 b1 = lds128(src + kImgStageBytes + 8);
         const uint32_t wa[8] = {a0.x, a0.y, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
         const uint32_t wb[8] = {b0.x, b0.y, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-        // every lane has read its inputs once the warp reconverges: the stage can be refilled
-        __syncwarp();
-        if (blk + kStages < it.nBlk) {
-            if (patchLeft || patchRight) fence_proxy_async();
-            issue_load(blk + kStages);
-        }
+        // The stage may be refilled once EVERY lane's loads have been performed: each lane releases the stage through an
+        // mbarrier (count 32) and lane 0 acquires it before re-arming the TMA barrier.  Program order plus __syncwarp() is
+        // not enough here -- with the refill issued straight after the loads, tools/dev/stress.py saw rare 8-row x 16-column
+        // blocks computed from the NEXT box's bytes (1080p, first block of an item).
+        // (the acquire + refill sit at ii == 10 below: by then the 32 arrivals have long drained and lane 0 never spins)
+        mbar_arrive(barStageEmpty + 8 * stage);
 
         // Ring position of this lane's row: input row i = 8*blk + hr lives in half (i / 11) & 1 at row t = i % 11.
         // Layout of a ring row (1056 bytes): two planes of 64 packed pairs, {E_h[a'], E_h[b']} at +0 and
@@ -276,6 +273,11 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA8, const CUt
                 else if (k > 0 && k <= 10) { hab[j] = fma2(ab, TAP(k), hab[j]); hsp[j] = fma2(sp, TAP(k), hsp[j]); }
             }
             if (ii == 10) {
+                if (blk + kStages < it.nBlk) {                      // refill this block's stage (see above)
+                    if (lane == 0) while (!mbar_test(barStageEmpty + 8 * stage, (uint32_t)(blk / kStages) & 1u)) { }
+                    if (patchLeft || patchRight) fence_proxy_async();
+                    issue_load(blk + kStages);
+                }
                 // first store of the block: the ring halves this block touches must have been drained by the consumer
                 // (waiting here, not at the top, lets the loads and the first 10 columns of math overlap the wait)
                 const int lastHalf = (blk * kBlkRows + kBlkRows - 1) / kTaps;
@@ -418,12 +420,11 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
 
 template <bool kMap>
 __global__ void __launch_bounds__(kCtaThreads, 2)
-ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmB8, const __grid_constant__ CUtensorMap tmB1,
+ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ FusedParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[kPairsPerCta][8];            // per pair: tmaFull[kStages], (pad), ringFull[2], ringEmpty[2]
+    __shared__ __align__(8) uint64_t bars[kPairsPerCta][8];            // per pair: tmaFull[kStages], stageEmpty[kStages], ringFull[2], ringEmpty[2]
 
     // shuffled from lane 0 so that the compiler knows the warp index (and everything derived from it: item, smem and
     // barrier addresses, TMA coordinates) is warp-uniform and keeps it on the uniform datapath
@@ -434,7 +435,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int pr = 0; pr < kPairsPerCta; ++pr)
-            for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[pr][i]), i < 4 ? 1 : 32);   // TMA barriers: 1 arrival; ring full/empty: all 32 lanes
+            for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[pr][i]), i < kStages ? 1 : 32);   // TMA barriers: 1 arrival; stage-empty, ring full/empty: all 32 lanes
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -458,7 +459,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA8, const __grid_constan
         if (item >= p.items) return;
         ItemCoords it; float ca, cb;
         decode_item(p, item, it, ca, cb);
-        producer_warp(&tmA8, &tmA1, &tmB8, &tmB1, p, it, lane, pairSmem, barBase, barBase + 32, barBase + 48, ca, cb);
+        producer_warp(&tmA, &tmB, p, it, lane, pairSmem, barBase, barBase + 32, barBase + 48, ca, cb);
     }
 }
 
@@ -562,13 +563,12 @@ static cudaError_t set_smem_attr()
     return cudaFuncSetAttribute(ssim_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
 }
 
-cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA8, const CUtensorMap& tmA1,
-                         const CUtensorMap& tmB8, const CUtensorMap& tmB1, const FusedParams& p)
+cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p)
 {
     const long long ctas = (p.items + kPairsPerCta - 1) / kPairsPerCta;
     if (ctas <= 0 || ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (p.map) ssim_fused_kernel<true><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
-    else       ssim_fused_kernel<false><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA8, tmA1, tmB8, tmB1, p);
+    if (p.map) ssim_fused_kernel<true><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA, tmB, p);
+    else       ssim_fused_kernel<false><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 

@@ -73,8 +73,7 @@ struct FinalizeParams {
     double invCount;         // 1 / double(uint32(width*outRows))
 };
 
-cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA8, const CUtensorMap& tmA1,
-                         const CUtensorMap& tmB8, const CUtensorMap& tmB1, const FusedParams& p);
+cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p);
 cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames);
 // per-device preparation (sets the dynamic shared-memory limit on the CURRENT device) + kernel facts
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm);
