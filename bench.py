@@ -245,6 +245,28 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
                                           fs.data_ptr(), fv.data_ptr()), 5)
     out["1080p_batch_512_per_gpu_with_maps"] = {"ms": round(ms, 3), "mpix_per_s": round(world * F * w * h / ms / 1e3, 1), "scaling": "weak",
                                                 "ssim_first_last": [float(fv[0].item()), float(fv[-1].item())]}
+    del a, b, m
+
+    # 16-bit pixels (L = 65535), 32 x 4K pairs with maps per GPU; pixels = 257 x the 8-bit synthetic
+    # frames, so the per-frame SSIM must equal the 8-bit one (scale invariance) -- reported next to it
+    F = 32
+    w, h = 3840, 2160
+    a8 = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    b8 = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    a = torch.empty((F, h, w), dtype=torch.int16, device=dev)
+    b = torch.empty((F, h, w), dtype=torch.int16, device=dev)
+    m = torch.empty((F, h, w), dtype=torch.float32, device=dev)
+    fv16 = torch.empty(F, dtype=torch.float32, device=dev)
+    for f in range(F):
+        api.synth_fill(local, sh, a8.data_ptr(), w, b8.data_ptr(), w, w, h, 0, rank * F + f)
+        a[f] = (a8.to(torch.int32) * 257).to(torch.int16)          # bit pattern of the uint16 value
+        b[f] = (b8.to(torch.int32) * 257).to(torch.int16)
+    api.compute_device(local, sh, w, h, 0, h, 1, a8.data_ptr(), w, 0, b8.data_ptr(), w, 0, None, 0, 0, None, val.data_ptr())
+    ms = timed(lambda: api.compute_device_u16(local, sh, w, h, 0, h, F, a.data_ptr(), 2 * w, 2 * w * h, b.data_ptr(), 2 * w, 2 * w * h,
+                                              m.data_ptr(), w, w * h, None, fv16.data_ptr()), 5)
+    torch.cuda.synchronize()
+    out["4k_u16_batch_32_per_gpu_with_maps"] = {"ms": round(ms, 3), "mpix_per_s": round(world * F * w * h / ms / 1e3, 1), "scaling": "weak",
+                                                "ssim_last_u16": float(fv16[-1].item()), "ssim_last_same_frame_u8": float(val.item())}
     return out
 
 

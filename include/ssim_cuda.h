@@ -101,6 +101,27 @@ int ssim_cuda_compute_device(int device, void* stream,
                              float* dMap, size_t mapPitch, size_t mapFrameStride,
                              double* dSums, float* dSsim);
 
+/*
+ * 16-bit pixels (dynamic range L = 65535: C1 = (0.01*65535)^2, C2 = (0.03*65535)^2), the extension the reference names but
+ * does not implement (reference README.md:107-111; L is hard-wired to 255 at src/ssim.cpp:958, retrieve_tile reads bytes at
+ * src/ssim.cpp:515-516).  Same kernel, same window, same border rule.  There is no reference implementation to compare
+ * with: parity is pinned through the scale invariance SSIM_16(257*a, 257*b) == SSIM_8(a, b) and the 16-bit oracle.
+ *
+ * ssim_cuda_compute_u16():        like ssim_cuda_compute(); stepA/strideA/stepB/strideB are in uint16 ELEMENTS (signed).
+ * ssim_cuda_compute_device_u16(): like ssim_cuda_compute_device(); pitches and frame strides in BYTES, multiples of 16.
+ */
+int ssim_cuda_compute_u16(int device, uint32_t width, uint32_t height,
+                          const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                          const uint16_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                          float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                          float* ssim);
+int ssim_cuda_compute_device_u16(int device, void* stream,
+                                 uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,
+                                 const uint16_t* dA, size_t pitchA, size_t frameStrideA,
+                                 const uint16_t* dB, size_t pitchB, size_t frameStrideB,
+                                 float* dMap, size_t mapPitch, size_t mapFrameStride,
+                                 double* dSums, float* dSsim);
+
 /* Number of kernels the previous ssim_cuda_compute_device() call on this thread launched (for bench.py) */
 int ssim_cuda_last_launch_count(void);
 

@@ -47,6 +47,8 @@ def oracle_lib():
                                         C.c_void_p, C.c_ssize_t, C.c_ssize_t,
                                         C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]
     lib.ssim_oracle_compute.restype = C.c_int
+    lib.ssim_oracle_compute_u16.argtypes = lib.ssim_oracle_compute.argtypes
+    lib.ssim_oracle_compute_u16.restype = C.c_int
     lib.ssim_oracle_taps.argtypes = [C.POINTER(C.c_double), C.c_int]
     lib.ssim_oracle_taps.restype = None
     lib.ssim_oracle_num_threads.restype = C.c_int
@@ -83,6 +85,20 @@ def oracle_ssim(a, b, want_map=False, taps=TAPS_TABLE, step_a=1, step_b=1, strid
                                           b.ctypes.data + b_off, step_b, stride_b,
                                           m.ctypes.data if want_map else None, 1, width,
                                           taps, C.byref(s), C.byref(d))
+    if rc != 0:
+        raise OSError(rc, os.strerror(rc))
+    return np.float32(s.value), d.value, m
+
+
+def oracle_ssim_u16(a, b, want_map=False, taps=TAPS_TABLE):
+    """16-bit restatement (L = 65535) on contiguous uint16 arrays.  Returns (ssim_float32, sum_double, map or None)."""
+    assert a.dtype == np.uint16 and b.dtype == np.uint16 and a.flags.c_contiguous and b.flags.c_contiguous
+    height, width = a.shape
+    m = np.empty((height, width), dtype=np.float32) if want_map else None
+    s = C.c_float()
+    d = C.c_double()
+    rc = oracle_lib().ssim_oracle_compute_u16(width, height, a.ctypes.data, 1, width, b.ctypes.data, 1, width,
+                                              m.ctypes.data if want_map else None, 1, width, taps, C.byref(s), C.byref(d))
     if rc != 0:
         raise OSError(rc, os.strerror(rc))
     return np.float32(s.value), d.value, m

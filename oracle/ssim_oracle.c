@@ -92,11 +92,17 @@ static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ?
  *   - mean = sum / double(width*height), width*height a uint32 product; returned as float
  *                                                                 (src/ssim.cpp:1102)
  */
-int ssim_oracle_compute(uint32_t width, uint32_t height,
-                        const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
-                        const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
-                        float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
-                        int tapsMode, float* ssim, double* sumOut)
+/* pixel (x,y) of an image whose step/stride are in ELEMENTS of 1 or 2 bytes */
+static double fetch(const void* img, int elemBytes, ptrdiff_t idx)
+{
+    return elemBytes == 2 ? (double)((const uint16_t*)img)[idx] : (double)((const uint8_t*)img)[idx];
+}
+
+static int oracle_core(uint32_t width, uint32_t height, int elemBytes, double L,
+                       const void* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                       const void* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                       float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                       int tapsMode, float* ssim, double* sumOut)
 {
     if (ssim == NULL && map == NULL && sumOut == NULL)
         return EINVAL;                                   /* src/ssim.cpp:962-966 */
@@ -108,8 +114,8 @@ int ssim_oracle_compute(uint32_t width, uint32_t height,
     double taps[TAPS * TAPS];
     ssim_oracle_taps(taps, tapsMode);
 
-    const double c1 = (0.01 * 255) * (0.01 * 255);
-    const double c2 = (0.03 * 255) * (0.03 * 255);
+    const double c1 = (0.01 * L) * (0.01 * L);           /* src/ssim.cpp:956-960 with L = 255 */
+    const double c2 = (0.03 * L) * (0.03 * L);
 
     const int W = (int)width, H = (int)height;
     const int PW = W + 2 * RADIUS;
@@ -126,8 +132,8 @@ int ssim_oracle_compute(uint32_t width, uint32_t height,
         for (int x = -RADIUS; x < W + RADIUS; ++x) {
             const int sx = clampi(x, 0, W - 1);
             const size_t d = (size_t)(y + RADIUS) * PW + (size_t)(x + RADIUS);
-            pa[d] = (double)a[(ptrdiff_t)sx * stepA + (ptrdiff_t)sy * strideA];
-            pb[d] = (double)b[(ptrdiff_t)sx * stepB + (ptrdiff_t)sy * strideB];
+            pa[d] = fetch(a, elemBytes, (ptrdiff_t)sx * stepA + (ptrdiff_t)sy * strideA);
+            pb[d] = fetch(b, elemBytes, (ptrdiff_t)sx * stepB + (ptrdiff_t)sy * strideB);
         }
     }
 
@@ -172,6 +178,27 @@ int ssim_oracle_compute(uint32_t width, uint32_t height,
     if (ssim != NULL)
         *ssim = (float)(sum / (double)(uint32_t)(width * height));
     return 0;
+}
+
+int ssim_oracle_compute(uint32_t width, uint32_t height,
+                        const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                        const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                        float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                        int tapsMode, float* ssim, double* sumOut)
+{
+    return oracle_core(width, height, 1, 255.0, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, tapsMode, ssim, sumOut);
+}
+
+/* 16-bit pixels, L = 65535: the extension the reference's README names (README.md:107-111) but does not implement.
+ * PARITY UNPINNED against the reference (there is nothing to run); pinned instead by the scale invariance
+ * SSIM_16(257 a, 257 b) == SSIM_8(a, b), which tests/test_oracle.py checks against the pinned 8-bit path. */
+int ssim_oracle_compute_u16(uint32_t width, uint32_t height,
+                            const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                            const uint16_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                            float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                            int tapsMode, float* ssim, double* sumOut)
+{
+    return oracle_core(width, height, 2, 65535.0, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, tapsMode, ssim, sumOut);
 }
 
 int ssim_oracle_num_threads(void)

@@ -25,6 +25,13 @@ int ssim_oracle_compute(uint32_t width, uint32_t height,
                         float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
                         int tapsMode, float* ssim, double* sumOut);
 
+/* 16-bit pixels (L = 65535); step/stride in uint16 elements.  Parity unpinned against the reference (not implemented there). */
+int ssim_oracle_compute_u16(uint32_t width, uint32_t height,
+                            const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                            const uint16_t* b, ptrdiff_t stepB, ptrdiff_t strideB,
+                            float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
+                            int tapsMode, float* ssim, double* sumOut);
+
 int ssim_oracle_num_threads(void);
 
 #ifdef __cplusplus

@@ -53,6 +53,10 @@ def cuda_lib():
                                              u8p, C.c_size_t, C.c_size_t, u8p, C.c_size_t, C.c_size_t,
                                              f32p, C.c_size_t, C.c_size_t, f64p, f32p]
     lib.ssim_cuda_compute_device.restype = C.c_int
+    lib.ssim_cuda_compute_u16.argtypes = lib.ssim_cuda_compute.argtypes
+    lib.ssim_cuda_compute_u16.restype = C.c_int
+    lib.ssim_cuda_compute_device_u16.argtypes = lib.ssim_cuda_compute_device.argtypes
+    lib.ssim_cuda_compute_device_u16.restype = C.c_int
     lib.ssim_cuda_last_launch_count.restype = C.c_int
     lib.ssim_cuda_compute_strips.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, u8p, C.c_ssize_t, C.c_ssize_t,
                                              u8p, C.c_ssize_t, C.c_ssize_t, f32p, C.c_ssize_t, C.c_ssize_t, C.POINTER(C.c_float)]
@@ -117,6 +121,28 @@ def compute_device(device, stream, width, src_rows, out_y0, out_rows, frames, d_
     """ssim_cuda_compute_device(): raw device addresses (ints), asynchronous on `stream` (int handle or None)."""
     _check(cuda_lib().ssim_cuda_compute_device(device, stream, width, src_rows, out_y0, out_rows, frames, d_a, pitch_a, fstride_a,
                                               d_b, pitch_b, fstride_b, d_map, map_pitch, map_fstride, d_sums, d_ssim))
+
+
+def compute_device_u16(device, stream, width, src_rows, out_y0, out_rows, frames, d_a, pitch_a, fstride_a, d_b, pitch_b, fstride_b,
+                       d_map=None, map_pitch=0, map_fstride=0, d_sums=None, d_ssim=None):
+    """ssim_cuda_compute_device_u16(): 16-bit planes, pitches and frame strides in BYTES."""
+    _check(cuda_lib().ssim_cuda_compute_device_u16(device, stream, width, src_rows, out_y0, out_rows, frames, d_a, pitch_a, fstride_a,
+                                                  d_b, pitch_b, fstride_b, d_map, map_pitch, map_fstride, d_sums, d_ssim))
+
+
+def compute_u16(a, b, want_map=False, want_ssim=True, width=None, height=None, step_a=1, step_b=1, stride_a=None, stride_b=None,
+                a_off=0, b_off=0, device=0):
+    """ssim_cuda_compute_u16() on numpy uint16 buffers; steps/strides/offsets in uint16 ELEMENTS.  Returns (ssim or None, map or None)."""
+    if width is None:
+        height, width = a.shape[:2]
+    stride_a = stride_a if stride_a is not None else width * step_a
+    stride_b = stride_b if stride_b is not None else width * step_b
+    m = np.empty((height, width), dtype=np.float32) if want_map else None
+    out = C.c_float()
+    _check(cuda_lib().ssim_cuda_compute_u16(device, width, height, a.ctypes.data + 2 * a_off, step_a, stride_a,
+                                           b.ctypes.data + 2 * b_off, step_b, stride_b,
+                                           m.ctypes.data if want_map else None, 1, width, C.byref(out) if want_ssim else None))
+    return (np.float32(out.value) if want_ssim else None), m
 
 
 def compute_strips(devices, a, b, want_map=False):

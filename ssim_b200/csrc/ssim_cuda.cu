@@ -126,15 +126,15 @@ EncodeTiledFn encode_fn()
 }
 
 int make_plane_map(CUtensorMap* tm, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
-                   size_t frameStride, uint32_t boxRows)
+                   size_t frameStride, uint32_t boxRows, int elemBytes = 1)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(EIO, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3]    = {width, rows, frames};
     const cuuint64_t strides[2] = {pitch, frames > 1 ? frameStride : (cuuint64_t)pitch * rows};
-    const cuuint32_t box[3]     = {(cuuint32_t)ssimk::kBoxW, boxRows, 1};
+    const cuuint32_t box[3]     = {(cuuint32_t)(elemBytes == 2 ? ssimk::PixGeo<true>::kBoxElems : ssimk::PixGeo<false>::kBoxElems), boxRows, 1};
     const cuuint32_t estr[3]    = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+    CUresult r = enc(tm, elemBytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EIO, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u pitch %zu", (int)r, width, rows, frames, pitch);
@@ -291,7 +291,7 @@ long long plan_items(const Context* c, uint32_t width, uint32_t outRows, uint32_
 int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
                         uint32_t frames, const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB,
                         size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim,
-                        const ChunkPlan* chunk = nullptr)
+                        const ChunkPlan* chunk = nullptr, int elemBytes = 1)
 {
     g_lastLaunches = 0;
     if (width == 0 || srcRows == 0 || outRows == 0 || frames == 0) return fail(EINVAL, "width, rows and frames must be non-zero");
@@ -301,7 +301,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (width > 0x7fffff00u || srcRows > 0x7fffff00u) return fail(EINVAL, "dimensions too large");
     if (((uintptr_t)dA | (uintptr_t)dB | pitchA | pitchB) & 15) return fail(EINVAL, "plane base addresses and pitches must be multiples of 16 bytes");
     if (frames > 1 && ((frameStrideA | frameStrideB) & 15)) return fail(EINVAL, "frame strides must be multiples of 16 bytes");
-    if (pitchA < width || pitchB < width) return fail(EINVAL, "pitch smaller than width");
+    if (pitchA < (size_t)width * elemBytes || pitchB < (size_t)width * elemBytes) return fail(EINVAL, "pitch smaller than width");
     if (dMap && mapPitch < width) return fail(EINVAL, "map pitch smaller than width");
 
     int segRows, segs;
@@ -321,12 +321,13 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
         if (chunk->itemsOut) *chunk->itemsOut = items;
     } else {
         if ((rc = get_partials(c, stream, (size_t)items * sizeof(double), &partials))) return rc;
-        if ((rc = make_plane_map(&local[0], dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows))) return rc;
-        if ((rc = make_plane_map(&local[1], dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows))) return rc;
+        if ((rc = make_plane_map(&local[0], dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows, elemBytes))) return rc;
+        if ((rc = make_plane_map(&local[1], dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows, elemBytes))) return rc;
     }
 
     ssimk::FusedParams p;
     memset(&p, 0, sizeof(p));
+    p.u16 = elemBytes == 2;
     p.a = dA; p.b = dB;
     p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
     p.pitchB = (long long)pitchB; p.frameStrideB = (long long)frameStrideB;
@@ -378,17 +379,20 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Brings one strided image into a canonical plane (dense rows, 16-byte aligned pitch) in device memory.
 // On return *plane/*pitch describe it; it is either the caller's own memory (already canonical) or ctx scratch.
 int canonical_plane(Context* c, cudaStream_t s, const uint8_t* img, ptrdiff_t step, ptrdiff_t stride, uint32_t W, uint32_t H,
-                    Buffer& planeBuf, Buffer& rawBuf, const uint8_t** plane, size_t* pitch, bool luma = false)
+                    Buffer& planeBuf, Buffer& rawBuf, const uint8_t** plane, size_t* pitch, bool luma = false, int elemBytes = 1)
 {
+    // elemBytes == 2: 16-bit pixels; `step`/`stride` are BYTE distances in every case
     // luma: `img` points at the R byte of interleaved RGB(A) pixels, three channels are read per pixel
     auto pack = [&](uint8_t* dst, long long dstPitch, const uint8_t* src, long long st, long long sd) {
         return luma ? ssimk::launch_pack_luma(s, dst, dstPitch, src, st, sd, (int)W, (int)H)
-                    : ssimk::launch_pack_u8(s, dst, dstPitch, src, st, sd, (int)W, (int)H);
+             : elemBytes == 2 ? ssimk::launch_pack_u16(s, dst, dstPitch, src, st, sd, (int)W, (int)H)
+                              : ssimk::launch_pack_u8(s, dst, dstPitch, src, st, sd, (int)W, (int)H);
     };
-    const ptrdiff_t extra = luma ? 2 : 0;                      // bytes read beyond the addressed one
+    const ptrdiff_t extra = luma ? 2 : elemBytes - 1;          // bytes read beyond the addressed one
+    const size_t rowBytes = (size_t)W * elemBytes;
     const Where where = classify(img);
-    const size_t canonPitch = align_up(W, 16);
-    if (!luma && where == Where::Device && step == 1 && stride >= (ptrdiff_t)W && (stride & 15) == 0 && ((uintptr_t)img & 15) == 0) {
+    const size_t canonPitch = align_up(rowBytes, 16);
+    if (!luma && where == Where::Device && step == elemBytes && stride >= (ptrdiff_t)rowBytes && (stride & 15) == 0 && ((uintptr_t)img & 15) == 0) {
         *plane = img; *pitch = (size_t)stride;
         return 0;
     }
@@ -396,8 +400,8 @@ int canonical_plane(Context* c, cudaStream_t s, const uint8_t* img, ptrdiff_t st
     if (rc) return rc;
     uint8_t* dst = (uint8_t*)planeBuf.ptr;
     *plane = dst; *pitch = canonPitch;
-    if (!luma && where == Where::Host && step == 1 && stride >= (ptrdiff_t)W) {
-        CU_TRY(cudaMemcpy2DAsync(dst, canonPitch, img, (size_t)stride, W, H, cudaMemcpyHostToDevice, s));
+    if (!luma && where == Where::Host && step == elemBytes && stride >= (ptrdiff_t)rowBytes) {
+        CU_TRY(cudaMemcpy2DAsync(dst, canonPitch, img, (size_t)stride, rowBytes, H, cudaMemcpyHostToDevice, s));
         return 0;
     }
     if (where == Where::Device) {
@@ -442,15 +446,15 @@ struct GeneralJob {
 
 int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, uint32_t outRows, const uint8_t* a, ptrdiff_t stepA,
                     ptrdiff_t strideA, const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep,
-                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job, bool luma = false)
+                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job, bool luma = false, int elemBytes = 1)
 {
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const uint8_t *pa, *pb;
     size_t pitchA, pitchB;
     int rc;
-    if ((rc = canonical_plane(c, s, a, stepA, strideA, W, srcRows, c->planeA, c->rawA, &pa, &pitchA, luma))) return rc;
-    if ((rc = canonical_plane(c, s, b, stepB, strideB, W, srcRows, c->planeB, c->rawB, &pb, &pitchB, luma))) return rc;
+    if ((rc = canonical_plane(c, s, a, stepA, strideA, W, srcRows, c->planeA, c->rawA, &pa, &pitchA, luma, elemBytes))) return rc;
+    if ((rc = canonical_plane(c, s, b, stepB, strideB, W, srcRows, c->planeB, c->rawB, &pb, &pitchB, luma, elemBytes))) return rc;
 
     // map destination: write straight into a canonical device map of the caller, else into scratch
     float* dMap = nullptr;
@@ -472,7 +476,7 @@ int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, ui
     float* dSsim = (float*)((char*)c->scalars.ptr + 8);
 
     rc = compute_device_impl(c, s, W, srcRows, outY0, outRows, 1, pa, pitchA, 0, pb, pitchB, 0, dMap, dMapPitch, 0, dSum,
-                             wantSsim ? dSsim : nullptr);
+                             wantSsim ? dSsim : nullptr, nullptr, elemBytes);
     if (rc) return rc;
 
     job->c = c; job->W = W; job->outRows = outRows; job->map = map; job->mapStep = mapStep; job->mapStride = mapStride;
@@ -598,6 +602,22 @@ int compute_general(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdif
         return compute_pipelined(c, W, H, a, strideA, b, strideB, map, mapStride, ssim);
     GeneralJob job;
     int rc = enqueue_general(c, W, H, 0, H, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job);
+    if (rc) return rc;
+    float hostSsim = 0.f;
+    if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = finish_general(job))) return rc;
+    if (ssim) *ssim = hostSsim;
+    return 0;
+}
+
+// 16-bit pixels: same machinery, element size 2, blocking single-shot path
+int compute_general_u16(Context* c, uint32_t W, uint32_t H, const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA, const uint16_t* b,
+                        ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
+{
+    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    GeneralJob job;
+    int rc = enqueue_general(c, W, H, 0, H, (const uint8_t*)a, 2 * stepA, 2 * strideA, (const uint8_t*)b, 2 * stepB, 2 * strideB, map, mapStep,
+                             mapStride, ssim != nullptr, &job, false, 2);
     if (rc) return rc;
     float hostSsim = 0.f;
     if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -860,6 +880,31 @@ int ssim_cuda_compute_device(int device, void* stream, uint32_t width, uint32_t 
     CU_TRY(cudaSetDevice(device));
     return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, frames, dA, pitchA, frameStrideA, dB, pitchB,
                                frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim);
+}
+
+int ssim_cuda_compute_u16(int device, uint32_t width, uint32_t height, const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
+                          const uint16_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
+{
+    if (ssim == nullptr && map == nullptr) return fail(EINVAL, "both ssim and map are NULL, nothing would be computed");
+    if (a == nullptr || b == nullptr) return fail(EINVAL, "image pointer is NULL");
+    if (width == 0 || height == 0) return fail(EINVAL, "width and height must be non-zero");
+    if (((uintptr_t)a | (uintptr_t)b) & 1) return fail(EINVAL, "16-bit images must be 2-byte aligned");
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    return compute_general_u16(c, width, height, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim);
+}
+
+int ssim_cuda_compute_device_u16(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,
+                                 const uint16_t* dA, size_t pitchA, size_t frameStrideA, const uint16_t* dB, size_t pitchB, size_t frameStrideB,
+                                 float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim)
+{
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, frames, (const uint8_t*)dA, pitchA, frameStrideA,
+                               (const uint8_t*)dB, pitchB, frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim, nullptr, 2);
 }
 
 int ssim_cuda_last_launch_count(void) { return g_lastLaunches; }

@@ -121,6 +121,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
 // flat regions (DESIGN.md "Numerics").  Any integer works; both warps of a pair must of course use the same one.
 __device__ __forceinline__ uint32_t div_u32(uint32_t n, uint32_t mul, uint32_t shift) { return mul ? __umulhi(n, mul) >> shift : n; }
 
+template <bool kU16>
 __device__ __forceinline__ void decode_item(const FusedParams& p, uint32_t item, ItemCoords& it, float& ca, float& cb)
 {
     const uint32_t q1 = div_u32(item, p.bandsMul, p.bandsShift);       // item / bands          (fast_div() constants)
@@ -136,18 +137,23 @@ __device__ __forceinline__ void decode_item(const FusedParams& p, uint32_t item,
     it.nBlk    = (it.nBodies * kTaps + kBlkRows - 1) / kBlkRows;
     const int cx = min(it.bx + kBandW / 2, p.width - 1);
     const int cy = min(max(it.oy0, 0), p.srcRows - 1);
-    ca = (float)__ldg(p.a + (long long)it.frame * p.frameStrideA + (long long)cy * p.pitchA + cx);
-    cb = (float)__ldg(p.b + (long long)it.frame * p.frameStrideB + (long long)cy * p.pitchB + cx);
+    const uint8_t* pa = p.a + (long long)it.frame * p.frameStrideA + (long long)cy * p.pitchA;
+    const uint8_t* pb = p.b + (long long)it.frame * p.frameStrideB + (long long)cy * p.pitchB;
+    if (kU16) { ca = (float)__ldg((const uint16_t*)pa + cx); cb = (float)__ldg((const uint16_t*)pb + cx); }
+    else      { ca = (float)__ldg(pa + cx);                  cb = (float)__ldg(pb + cx); }
 }
 
 // ---- producer: TMA + horizontal pass
+template <bool kU16>
 __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUtensorMap* tmB, const FusedParams& p, const ItemCoords& it, int lane,
                                               uint32_t pairSmem, uint32_t barTma, uint32_t barFull, uint32_t barEmpty, float ca, float cb)
 {
+    typedef PixGeo<kU16> G;
+    constexpr int kBoxW = G::kBoxBytes, kImgStageBytes = G::kImgStageBytes, kStageBytes = G::kStageBytes;   // shadow the 8-bit constants
     const uint32_t ringBase = pairSmem + kStages * kStageBytes;
     const uint32_t barStageEmpty = barTma + 8 * kStages;      // per stage: "all 32 lanes have read it" (count 32)
 
-    // One TMA load = an 8-row box x bytes [bx-16, bx+112) of both images.  A block needs rows [y, y+8) with y = inY0 + 8*blk,
+    // One TMA load = an 8-row box x bytes [bx-16, bx+112) of both images (16-bit: elements [bx-8, bx+72)).  A block needs rows [y, y+8) with y = inY0 + 8*blk,
     // rows outside the plane replicating the nearest one (src/ssim.cpp:562-582): the distinct rows it needs always fit in
     // the 8-row box starting at clamp(y, 0, srcRows-8), so edge blocks load that box and each lane reads the row
     // clamp(y + hr) of it.  Columns outside the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
@@ -160,8 +166,8 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             const uint32_t dst = pairSmem + stage * kStageBytes;
             const int y0 = min(max(it.inY0 + blk * kLoadRows, 0), lastBoxY);
             mbar_arrive_expect_tx(bar, kStageBytes);
-            tma_load_3d(dst, tmA, it.bx - kBoxLeft, y0, it.frame, bar);
-            tma_load_3d(dst + kImgStageBytes, tmB, it.bx - kBoxLeft, y0, it.frame, bar);
+            tma_load_3d(dst, tmA, it.bx - G::kBoxLeftElems, y0, it.frame, bar);
+            tma_load_3d(dst + kImgStageBytes, tmB, it.bx - G::kBoxLeftElems, y0, it.frame, bar);
         }
     };
     #pragma unroll
@@ -181,7 +187,9 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
 
     // this lane's share of a block: row hr, 16 output columns starting at 16*hq
     const int hr = lane >> 2, hq = lane & 3;
-    const uint32_t hSrcOff  = hr * kBoxW + hq * 16 + (kBoxLeft - 8);              // 32-byte window holding columns 16hq-8 .. 16hq+23
+    // 8-bit: 32-byte window holding columns 16hq-8 .. 16hq+23; 16-bit: 64-byte window holding columns 16hq-8 .. 16hq+23
+    const uint32_t hColOff  = kU16 ? hq * 32 : hq * 16 + (kBoxLeft - 8);
+    const uint32_t hSrcOff  = hr * kBoxW + hColOff;
 
     const bool patchLeft  = (it.bx == 0);
     const bool patchRight = (it.bx + kBandW + kHalo > p.width);
@@ -198,16 +206,30 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
         if (patchLeft || patchRight) {                       // warp-uniform; only the outermost bands
             if (lane < 2 * kLoadRows) {
                 const uint32_t row = stageBase + (lane >> 3) * kImgStageBytes + (lane & 7) * kBoxW;   // 2 images x 8 rows
-                if (patchLeft) {
-                    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row + kBoxLeft));
-                    #pragma unroll
-                    for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(row + kBoxLeft - k), "r"(v) : "memory");
-                }
-                if (patchRight) {
-                    const uint32_t last = row + kBoxLeft + (p.width - 1 - it.bx);
-                    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(last));
-                    #pragma unroll
-                    for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(last + k), "r"(v) : "memory");
+                if (kU16) {
+                    if (patchLeft) {
+                        uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(row + kBoxLeft));
+                        #pragma unroll
+                        for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u16 [%0], %1;" :: "r"(row + kBoxLeft - 2 * k), "r"(v) : "memory");
+                    }
+                    if (patchRight) {
+                        const uint32_t last = row + kBoxLeft + 2 * (p.width - 1 - it.bx);
+                        uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(last));
+                        #pragma unroll
+                        for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u16 [%0], %1;" :: "r"(last + 2 * k), "r"(v) : "memory");
+                    }
+                } else {
+                    if (patchLeft) {
+                        uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(row + kBoxLeft));
+                        #pragma unroll
+                        for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(row + kBoxLeft - k), "r"(v) : "memory");
+                    }
+                    if (patchRight) {
+                        const uint32_t last = row + kBoxLeft + (p.width - 1 - it.bx);
+                        uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(last));
+                        #pragma unroll
+                        for (int k = 1; k <= kHalo; ++k) asm volatile("st.shared.u8 [%0], %1;" :: "r"(last + k), "r"(v) : "memory");
+                    }
                 }
             }
             __syncwarp();
@@ -219,16 +241,26 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             const int y = it.inY0 + blk * kLoadRows;
             if (y < 0 || y > lastBoxY) {
                 const int y0 = min(max(y, 0), lastBoxY);
-                src = stageBase + (uint32_t)(min(max(y + hr, 0), p.srcRows - 1) - y0) * kBoxW + hq * 16 + (kBoxLeft - 8);
+                src = stageBase + (uint32_t)(min(max(y + hr, 0), p.srcRows - 1) - y0) * kBoxW + hColOff;
             }
         }
-        // the window starts 8 bytes into a 16-byte chunk: 8 + 16 + 8 byte loads
-        const uint2 a0 = lds64u(src), a2 = lds64u(src + 24);
-        const uint4 a1 = lds128(src + 8);
-        const uint2 b0 = lds64u(src + kImgStageBytes), b2 = lds64u(src + kImgStageBytes + 24);
-        const uint4 b1 = lds128(src + kImgStageBytes + 8);
-        const uint32_t wa[8] = {a0.x, a0.y, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
-        const uint32_t wb[8] = {b0.x, b0.y, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+        uint32_t wa[kU16 ? 16 : 8], wb[kU16 ? 16 : 8];
+        if (kU16) {
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 va = lds128(src + 16 * q), vb = lds128(src + kImgStageBytes + 16 * q);
+                wa[4 * q] = va.x; wa[4 * q + 1] = va.y; wa[4 * q + 2] = va.z; wa[4 * q + 3] = va.w;
+                wb[4 * q] = vb.x; wb[4 * q + 1] = vb.y; wb[4 * q + 2] = vb.z; wb[4 * q + 3] = vb.w;
+            }
+        } else {
+            // the window starts 8 bytes into a 16-byte chunk: 8 + 16 + 8 byte loads
+            const uint2 a0 = lds64u(src), a2 = lds64u(src + 24);
+            const uint4 a1 = lds128(src + 8);
+            const uint2 b0 = lds64u(src + kImgStageBytes), b2 = lds64u(src + kImgStageBytes + 24);
+            const uint4 b1 = lds128(src + kImgStageBytes + 8);
+            wa[0] = a0.x; wa[1] = a0.y; wa[2] = a1.x; wa[3] = a1.y; wa[4] = a1.z; wa[5] = a1.w; wa[6] = a2.x; wa[7] = a2.y;
+            wb[0] = b0.x; wb[1] = b0.y; wb[2] = b1.x; wb[3] = b1.y; wb[4] = b1.z; wb[5] = b1.w; wb[6] = b2.x; wb[7] = b2.y;
+        }
         // The stage may be refilled once EVERY lane's loads have been performed: each lane releases the stage through an
         // mbarrier (count 32) and lane 0 acquires it before re-arming the TMA barrier.  Program order plus __syncwarp() is
         // not enough here -- with the refill issued straight after the loads, tools/dev/stress.py saw rare 8-row x 16-column
@@ -254,13 +286,19 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
         u64 hab[16], hsp[16];
         #pragma unroll
         for (int ii = 0; ii < 26; ++ii) {                // input column 16hq - 5 + ii  = byte 3 + ii of the 32-byte window
-            const int byteIdx = ii + 3;
+            const int byteIdx = ii + 3;                     // 16-bit: halfword index
             float fa, fb;
-            switch (byteIdx & 3) {
-                case 0:  fa = magic_byte<0>(wa[byteIdx >> 2], magic); fb = magic_byte<0>(wb[byteIdx >> 2], magic); break;
-                case 1:  fa = magic_byte<1>(wa[byteIdx >> 2], magic); fb = magic_byte<1>(wb[byteIdx >> 2], magic); break;
-                case 2:  fa = magic_byte<2>(wa[byteIdx >> 2], magic); fb = magic_byte<2>(wb[byteIdx >> 2], magic); break;
-                default: fa = magic_byte<3>(wa[byteIdx >> 2], magic); fb = magic_byte<3>(wb[byteIdx >> 2], magic); break;
+            if (kU16) {
+                // 2^23 + pixel: the two pixel bytes under the two top bytes of the magic word (PRMT with an immediate selector)
+                if (byteIdx & 1) { fa = __uint_as_float(__byte_perm(wa[byteIdx >> 1], magic, 0x7632)); fb = __uint_as_float(__byte_perm(wb[byteIdx >> 1], magic, 0x7632)); }
+                else             { fa = __uint_as_float(__byte_perm(wa[byteIdx >> 1], magic, 0x7610)); fb = __uint_as_float(__byte_perm(wb[byteIdx >> 1], magic, 0x7610)); }
+            } else {
+                switch (byteIdx & 3) {
+                    case 0:  fa = magic_byte<0>(wa[byteIdx >> 2], magic); fb = magic_byte<0>(wb[byteIdx >> 2], magic); break;
+                    case 1:  fa = magic_byte<1>(wa[byteIdx >> 2], magic); fb = magic_byte<1>(wb[byteIdx >> 2], magic); break;
+                    case 2:  fa = magic_byte<2>(wa[byteIdx >> 2], magic); fb = magic_byte<2>(wb[byteIdx >> 2], magic); break;
+                    default: fa = magic_byte<3>(wa[byteIdx >> 2], magic); fb = magic_byte<3>(wb[byteIdx >> 2], magic); break;
+                }
             }
             const u64 ab = add2(pack2(fa, fb), negMagic);          // (a - ca, b - cb), exact
             float a, b; unpack2(ab, a, b);
@@ -302,16 +340,17 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
 }
 
 // ---- consumer: vertical pass + formula + outputs
-template <bool kMap>
+template <bool kMap, bool kU16>
 __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCoords& it, int lane, uint32_t item, uint32_t pairSmem,
                                               uint32_t barFull, uint32_t barEmpty, float ca, float cb)
 {
-    const uint32_t ringBase = pairSmem + kStages * kStageBytes;
+    const uint32_t ringBase = pairSmem + kStages * PixGeo<kU16>::kStageBytes;
     u64 w2[6];
     #pragma unroll
     for (int d = 0; d < 6; ++d) w2[d] = pack2(p.g[d], p.g[d]);
     #define TAP(m) w2[(m) < 5 ? 5 - (m) : (m) - 5]
-    constexpr float c1 = 6.5025f, c2 = 58.5225f;          // (0.01*255)^2, (0.03*255)^2 as float: src/ssim.cpp:956-960
+    // (0.01*L)^2, (0.03*L)^2 as float, L = 255 (src/ssim.cpp:956-960) or 65535 (the 16-bit extension the reference's README names)
+    constexpr float c1 = kU16 ? 429483.6225f : 6.5025f, c2 = kU16 ? 3865352.6025f : 58.5225f;
 
     // this lane owns columns bx+lane and bx+32+lane (ring layout: see producer_warp); column c sits at 8*(c ^ (c>>4))
     const uint32_t vBase0 = ringBase + ((uint32_t)(lane ^ (lane >> 4)) << 3);
@@ -418,7 +457,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ItemCo
     if (lane == 0) p.partials[item] = total;
 }
 
-template <bool kMap>
+template <bool kMap, bool kU16>
 __global__ void __launch_bounds__(kCtaThreads, 2)
 ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ FusedParams p)
@@ -442,7 +481,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();                                                    // the only CTA-wide barrier
 
     const uint32_t item = blockIdx.x * kPairsPerCta + pair;           // < 2^31, checked by the host
-    const uint32_t pairSmem = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + pair * kPairSmemBytes;
+    const uint32_t pairSmem = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + pair * PixGeo<kU16>::kPairSmemBytes;
     const uint32_t barBase  = __shfl_sync(0xffffffffu, smem_u32(&bars[0][0]), 0) + pair * 64;
 
     // Register hand-over between the two warpgroups: every warp of a warpgroup must execute its setmaxnreg (so it comes
@@ -452,14 +491,14 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kConsumerRegs));
         if (item >= p.items) return;
         ItemCoords it; float ca, cb;
-        decode_item(p, item, it, ca, cb);
-        consumer_warp<kMap>(p, it, lane, item, pairSmem, barBase + 32, barBase + 48, ca, cb);
+        decode_item<kU16>(p, item, it, ca, cb);
+        consumer_warp<kMap, kU16>(p, it, lane, item, pairSmem, barBase + 32, barBase + 48, ca, cb);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kProducerRegs));
         if (item >= p.items) return;
         ItemCoords it; float ca, cb;
-        decode_item(p, item, it, ca, cb);
-        producer_warp(&tmA, &tmB, p, it, lane, pairSmem, barBase, barBase + 32, barBase + 48, ca, cb);
+        decode_item<kU16>(p, item, it, ca, cb);
+        producer_warp<kU16>(&tmA, &tmB, p, it, lane, pairSmem, barBase, barBase + 32, barBase + 48, ca, cb);
     }
 }
 
@@ -494,6 +533,16 @@ __global__ void pack_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, co
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x < width && y < height) dst[(long long)y * dstPitch + x] = src[(long long)x * step + (long long)y * stride];
+}
+
+// same for 16-bit pixels: src is a byte pointer, step/stride are BYTE distances (multiples of 2)
+__global__ void pack_u16_kernel(uint8_t* __restrict__ dst, long long dstPitch, const uint8_t* __restrict__ src,
+                                long long step, long long stride, int width, int height)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < width && y < height)
+        *(uint16_t*)(dst + (long long)y * dstPitch + 2 * x) = *(const uint16_t*)(src + (long long)x * step + (long long)y * stride);
 }
 
 // BT.601 luma of an interleaved RGB(A) image, integer arithmetic identical to the reference CLI's CPU loop
@@ -558,17 +607,24 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ dA, long long pitchA, ui
 // cudaFuncSetAttribute is per DEVICE: called from every device context's initialisation (current device = that device)
 static cudaError_t set_smem_attr()
 {
-    cudaError_t e = cudaFuncSetAttribute(ssim_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ssim_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(ssim_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<false>::kCtaSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ssim_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<false>::kCtaSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ssim_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<true>::kCtaSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ssim_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<true>::kCtaSmemBytes);
+    return e;
 }
 
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p)
 {
     const long long ctas = (p.items + kPairsPerCta - 1) / kPairsPerCta;
     if (ctas <= 0 || ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (p.map) ssim_fused_kernel<true><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA, tmB, p);
-    else       ssim_fused_kernel<false><<<(unsigned)ctas, kCtaThreads, kCtaSmemBytes, stream>>>(tmA, tmB, p);
+    if (p.u16) {
+        if (p.map) ssim_fused_kernel<true, true><<<(unsigned)ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p);
+        else       ssim_fused_kernel<false, true><<<(unsigned)ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p);
+    } else {
+        if (p.map) ssim_fused_kernel<true, false><<<(unsigned)ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p);
+        else       ssim_fused_kernel<false, false><<<(unsigned)ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p);
+    }
     return cudaGetLastError();
 }
 
@@ -583,12 +639,17 @@ cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm
     cudaError_t e = set_smem_attr();
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<true>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<true, false>)) != cudaSuccess) return e;
     if (regsMap) *regsMap = fa.numRegs;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<false, false>)) != cudaSuccess) return e;
     if (regsNoMap) *regsNoMap = fa.numRegs;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<true>, kCtaThreads, kCtaSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<true, false>, kCtaThreads, PixGeo<false>::kCtaSmemBytes);
+    if (e == cudaSuccess) {
+        int n16 = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<true, true>, kCtaThreads, PixGeo<true>::kCtaSmemBytes);
+        if (n16 < n) n = n16;
+    }
     if (ctasPerSm) *ctasPerSm = n;
     return e;
 }
@@ -600,6 +661,14 @@ cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch
 {
     const dim3 block(64, 4);
     pack_u8_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, step, stride, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_u16(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
+                            long long step, long long stride, int width, int height)
+{
+    const dim3 block(64, 4);
+    pack_u16_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, step, stride, width, height);
     return cudaGetLastError();
 }
 

@@ -35,7 +35,23 @@ constexpr int kRingBytes      = kRingRows * kRingRowBytes; // 23232
 constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;  // 27392
 constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;       // 109568 -> 2 CTAs (16 warps) per SM
 
+// Per pixel type geometry of the TMA stage (the ring and everything after the widening are identical).  16-bit pixels
+// (the extension the reference's README names): box rows of 80 elements = 160 bytes -- band column 0 sits
+// at byte 16 in both layouts, the innermost TMA coordinate bx-8 elements is again a multiple of 16 bytes, and since a
+// stage is one box only its start has to be 128-byte aligned.
+template <bool kU16> struct PixGeo {
+    static constexpr int kPixBytes      = kU16 ? 2 : 1;
+    static constexpr int kBoxBytes      = kU16 ? 160 : kBoxW;
+    static constexpr int kBoxElems      = kBoxBytes / kPixBytes;            // 128 / 80
+    static constexpr int kBoxLeftElems  = kBoxLeft / kPixBytes;             // 16 / 8
+    static constexpr int kImgStageBytes = kBoxBytes * kLoadRows;            // 1024 / 1280
+    static constexpr int kStageBytes    = 2 * kImgStageBytes;               // 2048 / 2560
+    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 27392 / 28416
+    static constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;    // 109568 / 113664 (2 CTAs/SM either way)
+};
+
 struct FusedParams {
+    int u16;                 // 0: 8-bit pixels, 1: 16-bit pixels (pitches and frame strides stay in BYTES)
     const uint8_t* a;        // raw planes (used only to fetch the per-item centring pixel)
     const uint8_t* b;
     long long pitchA, frameStrideA, pitchB, frameStrideB;
@@ -81,6 +97,8 @@ cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm
 // layout helpers
 cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
                            long long step, long long stride, int width, int height);
+cudaError_t launch_pack_u16(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
+                            long long step, long long stride, int width, int height);   // step/stride in bytes
 cudaError_t launch_pack_luma(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
                              long long step, long long stride, int width, int height);
 cudaError_t launch_deinterleave_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, long long planeStride, const uint8_t* src,

@@ -140,3 +140,24 @@ def test_reference_builds_are_what_they_claim():
     assert oracle.ref_lib("f64").ref_uses_double() == 1
     # AUTO on x86 picks FMA when available: mask has generic|auto at least
     assert oracle.ref_lib("f32").ref_select_impl(0) & 0x3 == 0x3
+
+
+def test_u16_oracle_scale_invariance():
+    """The 16-bit restatement (L = 65535; not implemented by the reference, README.md:107-111) is pinned through
+    SSIM_16(257 a, 257 b) == SSIM_8(a, b): C1 and C2 scale with L^2 and 65535 = 257 * 255."""
+    from oracle import oracle_ssim, oracle_ssim_u16
+    rng = np.random.default_rng(3)
+    for h, w in ((1, 1), (7, 19), (97, 131)):
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-25, 26, a.shape), 0, 255).astype(np.uint8)
+        for taps in (0, 1):
+            s8, d8, m8 = oracle_ssim(a, b, want_map=True, taps=taps)
+            s16, d16, m16 = oracle_ssim_u16(a.astype(np.uint16) * 257, b.astype(np.uint16) * 257, want_map=True, taps=taps)
+            assert abs(d8 - d16) <= 1e-9 * max(1.0, abs(d8)) and np.abs(m8 - m16).max() <= 1e-6 and abs(float(s8) - float(s16)) <= 1e-7
+    # genuinely 16-bit content: symmetric, 1.0 on identical images, below 1 otherwise
+    a = rng.integers(0, 65536, (33, 47), dtype=np.uint16)
+    b = np.clip(a.astype(int) + rng.integers(-3000, 3001, a.shape), 0, 65535).astype(np.uint16)
+    sab, _, _ = oracle_ssim_u16(a, b)
+    sba, _, _ = oracle_ssim_u16(b, a)
+    saa, _, maa = oracle_ssim_u16(a, a.copy(), want_map=True)
+    assert sab == sba and saa == np.float32(1.0) and (maa == 1.0).all() and sab < 1.0

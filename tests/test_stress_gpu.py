@@ -35,6 +35,27 @@ def _repeat(W, H, F, with_map, reps):
     return bad
 
 
+def test_bitwise_repeatable_u16():
+    import torch
+    from ssim_b200 import api
+    W, H, reps = 1920, 1080, 150
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(0, 65536, (H, W), generator=g, device="cuda", dtype=torch.int32)
+    b = (a + torch.randint(-4000, 4001, (H, W), generator=g, device="cuda", dtype=torch.int32)).clamp_(0, 65535)
+    a16, b16 = a.to(torch.int16).contiguous(), b.to(torch.int16).contiguous()
+    m = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    s = torch.empty(1, dtype=torch.float64, device="cuda")
+    ref = None
+    for _ in range(reps):
+        api.compute_device_u16(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, 1, a16.data_ptr(), 2 * W, 0, b16.data_ptr(), 2 * W, 0,
+                               m.data_ptr(), W, 0, s.data_ptr(), None)
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = (s.clone(), m.clone())
+        else:
+            assert torch.equal(s, ref[0]) and torch.equal(m, ref[1])
+
+
 @pytest.mark.parametrize("shape", [(1920, 1080, 1, False, 200), (1920, 1080, 1, True, 200), (336, 141, 7, True, 200),
                                    (256, 256, 1, True, 200), (3840, 2160, 1, True, 100), (1920, 1080, 24, True, 30)])
 def test_bitwise_repeatable(shape):
