@@ -73,7 +73,7 @@ __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t magic) { ret
 // ------------------------------------------------------------------------------------------------ fused kernel
 // Work item = (frame, row segment, 64-column band).  Each item is served by a PAIR of warps of the same CTA:
 //
-//   producer warp (warps 0-3)   TMA loads of 8-row u8 boxes into a 3-stage ring, clamp patching, u8 -> f32, products,
+//   producer warp (warps 0-3)   TMA loads of 8-row pixel boxes into a 2-stage ring, clamp patching, u8/u16 -> f32, products,
 //                               horizontal 11-tap pass; writes 8-row blocks of {E_h[a'], E_h[b']}, {E_h[(a'-b')^2], E_h[a'b']}
 //                               into a 22-row shared-memory ring = two halves of 11 rows (full/empty mbarrier per half)
 //   consumer warp (warps 4-7)   vertical 11-tap pass with eleven IN-PLACE accumulators per plane pair: its loop body is
@@ -83,7 +83,8 @@ __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t magic) { ret
 //
 // The two roles overlap in time (the consumer's dependent formula chain hides behind the producer's FMAs and vice versa),
 // setmaxnreg moves registers from the producers (96) to the consumers (160), and nothing is ever synchronised CTA-wide
-// after the prologue.
+// after the prologue.  Every hand-over (TMA stage full/empty, ring half full/empty) is an mbarrier on which each lane
+// releases its own accesses and each lane acquires for itself: see the protocol table in DESIGN.md section 4.
 struct ItemCoords {
     int frame, bx, oy0, nOut, inY0;
     int nBodies;    // 11-row bodies the consumer runs: ceil((nOut + 10) / 11)

@@ -13,7 +13,7 @@ constexpr int kBandW       = 64;   // output columns per warp work item (lane ow
 constexpr int kBlkRows     = 8;    // rows per TMA block / horizontal-pass block
 constexpr int kHalo        = 5;    // Gaussian radius (reference src/ssim.cpp:227)
 constexpr int kBoxW        = 128;  // TMA box width in bytes: 16 left margin + 64 columns + right margin; 128 so that every box
-                                   // row (and so every single-row edge load) lands on a 128-byte aligned shared-memory address
+                                   // row lands on a 128-byte aligned shared-memory address (TMA needs that of the box start)
 constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row: the innermost TMA coordinate (bx - 16) must be
                                    // a multiple of 16 bytes -- measured on B200: x = -16 works, x = -8 raises "illegal instruction"
                                    // (tools/dev/tma_probe.cu)
