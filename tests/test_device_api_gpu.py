@@ -173,3 +173,46 @@ def test_concurrent_calls_from_many_threads():
     torch.cuda.synchronize()
     for (ds, _, _), wv in zip(outs, want[:2]):
         assert abs(float(ds.item()) - float(wv[0])) <= GLOBAL_TOL
+
+
+def test_full_size_known_answers(golden):
+    """BASELINE.json configs[3]/[4] at their FULL sizes against values the unmodified reference produced here
+    (tests/golden/make_golden.py): the 16384x16384 pair as one image and as 8 row strips with halos, and frames
+    0 / 1 / 4095 of the 1080p sweep inside one batched launch.  Inputs come from the device-side synthetic recipe,
+    whose equality with the host recipe is checked in test_batch_of_frames_matches_per_frame_oracle."""
+    import torch
+    from ssim_b200 import parallel
+    st = torch.cuda.current_stream().cuda_stream
+    W = H = 16384
+    a = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    b = torch.empty_like(a)
+    api.synth_fill(0, st, a.data_ptr(), W, b.data_ptr(), W, W, H, 0, 0)
+    val = torch.empty(1, dtype=torch.float32, device="cuda")
+    sums = torch.empty(1, dtype=torch.float64, device="cuda")
+    api.compute_device(0, st, W, H, 0, H, 1, a.data_ptr(), W, 0, b.data_ptr(), W, 0, None, 0, 0, sums.data_ptr(), val.data_ptr())
+    torch.cuda.synchronize()
+    want = golden["synthetic"]["16384x16384_f0"]["ref_f64_auto"]
+    assert abs(float(val.item()) - want) <= GLOBAL_TOL
+    # 8 strips with 5 halo rows on interior edges: the partial sums add up to the single-image sum
+    total = 0.0
+    part = torch.empty(1, dtype=torch.float64, device="cuda")
+    for r in range(8):
+        s0, s1, oy, orows = parallel.strip_bounds(H, 8, r)
+        api.compute_device(0, st, W, s1 - s0, oy, orows, 1, a[s0:s1].data_ptr(), W, 0, b[s0:s1].data_ptr(), W, 0, None, 0, 0, part.data_ptr(), None)
+        torch.cuda.synchronize()
+        total += float(part.item())
+    assert abs(parallel.mean_from_partials(total, W, H) - want) <= GLOBAL_TOL
+    assert abs(total - float(sums.item())) <= 2e-7 * W * H
+    del a, b
+    # 1080p frames 0, 1, 4095 in one launch
+    w, h = 1920, 1080
+    frames = [0, 1, 4095]
+    fa = torch.empty((3, h, w), dtype=torch.uint8, device="cuda")
+    fb = torch.empty_like(fa)
+    for i, f in enumerate(frames):
+        api.synth_fill(0, st, fa[i].data_ptr(), w, fb[i].data_ptr(), w, w, h, 0, f)
+    fv = torch.empty(3, dtype=torch.float32, device="cuda")
+    api.compute_device(0, st, w, h, 0, h, 3, fa.data_ptr(), w, w * h, fb.data_ptr(), w, w * h, None, 0, 0, None, fv.data_ptr())
+    torch.cuda.synchronize()
+    for i, f in enumerate(frames):
+        assert abs(float(fv[i].item()) - golden["synthetic"]["1920x1080_f%d" % f]["ref_f64_auto"]) <= GLOBAL_TOL
