@@ -13,7 +13,8 @@ scaling); the timed region is bracketed by barrier + synchronize and the slowest
 Printed JSON (one line, rank 0):
   value      whole-job Mpix/s (all ranks' pixels / max-over-ranks device time), inputs and outputs in HBM
   e2e        same metric through the reference-facing API rmgr_ssim_compute_ssim() with pinned HOST buffers:
-             H2D of both images and D2H of the map + scalar inside the timed region, one blocking call per frame
+             H2D of both images and D2H of the map + scalar inside the timed region, one blocking call per frame,
+             the calls issued from --e2e-threads host threads (default 2; the API is re-entrant like the reference's)
   roofline   the fused kernel alone (CUDA events around K launches with no reduction kernel): algorithmic
              230 flop/pixel / duration vs the FP32 FFMA peak 148 SM x 128 lanes x 2 x sm_max_mhz
              (MEASURED_PEAKS.json has no FP32 figure; tools/microbench measured 97-99% of this nominal peak),
@@ -51,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary BASELINE.json configs (1080p, 16384^2 strips, 1080p batch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--e2e-threads", type=int, default=2, help="host threads issuing the blocking reference-API calls of the e2e leg")
     return ap.parse_args()
 
 
@@ -402,12 +404,29 @@ def run_ours(args):
     nA, nB, nM = hA.numpy(), hB.numpy(), hMap.numpy()
     os.environ["SSIM_CUDA_DEVICE"] = str(local)
 
+    # The reference API is re-entrant, and its own arm uses every host core: the step's F blocking calls are
+    # issued from E2E_THREADS host threads (ctypes drops the GIL), each frame by exactly one call; concurrent calls run
+    # on sibling contexts of the device and hide each other's pipeline fill and drain.
+    import threading
+    e2e_threads = max(1, args.e2e_threads)
+
     def e2e_step():
-        last = None
-        for f in range(F):
-            k = f % eF
-            last, _ = api.compute_ssim(nA[k], nB[k], ssim_map=nM[k])
-        return last
+        last = [None] * e2e_threads
+
+        def work(t):
+            for f in range(t, F, e2e_threads):
+                k = f % eF
+                last[t], _ = api.compute_ssim(nA[k], nB[k], ssim_map=nM[k])
+
+        if e2e_threads == 1:
+            work(0)
+        else:
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(e2e_threads)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        return last[(F - 1) % e2e_threads]
 
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(1):
@@ -451,7 +470,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": config(args, n),
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": F * 2 * npx, "d2h_bytes_per_step": F * (npx * 4 + 4),
-                    "api": "rmgr_ssim_compute_ssim (librmgr-ssim.so), one blocking call per 4K pair, pinned host buffers", "steps": e2e_steps},
+                    "api": "rmgr_ssim_compute_ssim (librmgr-ssim.so), one blocking call per 4K pair, pinned host buffers, calls issued from %d host thread(s)" % e2e_threads,
+                    "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": round(achieved, 2), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
                          "frac": round(achieved / fp32_peak, 4), "traffic": traffic,

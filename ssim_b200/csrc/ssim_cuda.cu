@@ -184,11 +184,8 @@ struct Context {
 std::mutex g_ctxMutex;
 std::map<int, Context*> g_ctx;
 
-int get_context(int device, Context** out)
+int create_context(int device, Context** out)
 {
-    std::lock_guard<std::mutex> lock(g_ctxMutex);
-    auto it = g_ctx.find(device);
-    if (it != g_ctx.end()) { *out = it->second; return 0; }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) { cudaGetLastError(); return fail(ENODEV, "no usable CUDA device (%s)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)); }
@@ -213,8 +210,67 @@ int get_context(int device, Context** out)
     int regsMap = 0, regsNoMap = 0, ctas = 0;
     CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &ctas));
     c->ctasPerSm = std::max(1, ctas);
+    *out = c;
+    return 0;
+}
+
+void destroy_context(Context* c)
+{
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (Buffer* b : {&c->planeA, &c->planeB, &c->rawA, &c->rawB, &c->map, &c->stage, &c->scalars, &c->chunkSums, &c->chunkSumsHost}) b->release();
+    for (int i = 0; i < Context::kMaxChunks; ++i) { if (c->evIn[i]) cudaEventDestroy(c->evIn[i]); if (c->evDone[i]) cudaEventDestroy(c->evDone[i]); }
+    if (c->streamIn) cudaStreamDestroy(c->streamIn);
+    if (c->streamOut) cudaStreamDestroy(c->streamOut);
+    for (auto& p : c->partials) p.second.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int get_context(int device, Context** out)
+{
+    std::lock_guard<std::mutex> lock(g_ctxMutex);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) { *out = it->second; return 0; }
+    Context* c = nullptr;
+    int rc = create_context(device, &c);
+    if (rc) return rc;
     g_ctx[device] = c;
     *out = c;
+    return 0;
+}
+
+// The blocking host-pointer calls use per-context scratch (planes, map, staging, streams), so one context serves one call
+// at a time.  Callers that invoke the API from several threads (the reference is re-entrant, SURVEY 8b "Threading") get up
+// to kHostContexts calls in flight per device: a busy primary context makes the call take (or lazily create) a sibling,
+// whose copies and kernels then overlap the first call's on the GPU -- two threads hide each other's pipeline fill and
+// drain and bring the host path close to the PCIe bound.
+const size_t kHostContexts = 3;
+std::map<int, std::vector<Context*>> g_hostCtx;     // siblings of g_ctx[device], guarded by g_ctxMutex
+
+int acquire_host_context(Context** c, std::unique_lock<std::mutex>* lock)
+{
+    Context* primary = *c;
+    *lock = std::unique_lock<std::mutex>(primary->hostPathMutex, std::try_to_lock);
+    if (lock->owns_lock()) return 0;
+    {
+        std::lock_guard<std::mutex> g(g_ctxMutex);
+        std::vector<Context*>& sib = g_hostCtx[primary->device];
+        for (Context* s : sib) {
+            *lock = std::unique_lock<std::mutex>(s->hostPathMutex, std::try_to_lock);
+            if (lock->owns_lock()) { *c = s; return 0; }
+        }
+        if (sib.size() + 1 < kHostContexts) {
+            Context* s = nullptr;
+            int rc = create_context(primary->device, &s);
+            if (rc) return rc;
+            sib.push_back(s);
+            *lock = std::unique_lock<std::mutex>(s->hostPathMutex);
+            *c = s;
+            return 0;
+        }
+    }
+    *lock = std::unique_lock<std::mutex>(primary->hostPathMutex);      // everything busy: queue on the primary
     return 0;
 }
 
@@ -592,7 +648,8 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
 int compute_general(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA, const uint8_t* b,
                     ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
 {
-    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    std::unique_lock<std::mutex> lock;
+    if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
     // pipelined path: plain-row host images (and host map) large enough for the overlap to pay.  Pageable memory works
     // too (the runtime stages it), pinned memory gets the full overlap.
     if ((uint64_t)W * H >= (1u << 21) && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
@@ -614,7 +671,8 @@ int compute_general(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdif
 int compute_general_u16(Context* c, uint32_t W, uint32_t H, const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA, const uint16_t* b,
                         ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
 {
-    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    std::unique_lock<std::mutex> lock;
+    if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
     GeneralJob job;
     int rc = enqueue_general(c, W, H, 0, H, (const uint8_t*)a, 2 * stepA, 2 * strideA, (const uint8_t*)b, 2 * stepB, 2 * strideB, map, mapStep,
                              mapStride, ssim != nullptr, &job, false, 2);
@@ -758,18 +816,10 @@ int ssim_cuda_init(int device)
 void ssim_cuda_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_ctxMutex);
-    for (auto& kv : g_ctx) {
-        Context* c = kv.second;
-        cudaSetDevice(c->device);
-        cudaDeviceSynchronize();
-        for (Buffer* b : {&c->planeA, &c->planeB, &c->rawA, &c->rawB, &c->map, &c->stage, &c->scalars, &c->chunkSums, &c->chunkSumsHost}) b->release();
-        for (int i = 0; i < Context::kMaxChunks; ++i) { if (c->evIn[i]) cudaEventDestroy(c->evIn[i]); if (c->evDone[i]) cudaEventDestroy(c->evDone[i]); }
-        if (c->streamIn) cudaStreamDestroy(c->streamIn);
-        if (c->streamOut) cudaStreamDestroy(c->streamOut);
-        for (auto& p : c->partials) p.second.release();
-        if (c->stream) cudaStreamDestroy(c->stream);
-        delete c;
-    }
+    for (auto& kv : g_ctx) destroy_context(kv.second);
+    for (auto& kv : g_hostCtx)
+        for (Context* s : kv.second) destroy_context(s);
+    g_hostCtx.clear();
     g_ctx.clear();
     {
         std::lock_guard<std::mutex> nlock(g_nccl.mutex);
@@ -811,7 +861,8 @@ int ssim_cuda_compute_luma(int device, uint32_t width, uint32_t height, const ui
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    std::unique_lock<std::mutex> lock;
+    if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
     GeneralJob job;
     rc = enqueue_general(c, width, height, 0, height, rgbA, stepA, strideA, rgbB, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job, true);
     if (rc) return rc;
@@ -834,7 +885,8 @@ int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(c->hostPathMutex);
+    std::unique_lock<std::mutex> lock;
+    if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
     CU_TRY(cudaSetDevice(device));
     cudaStream_t s = c->stream;
     const size_t rawPitch = align_up(rowBytes, 16), pitch = align_up(width, 16), plane = pitch * height;
