@@ -264,6 +264,30 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
     out["16384x16384_strips_with_map"] = {"ms": round(ms, 4), "mpix_per_s": round(W16 * W16 / ms / 1e3, 1), "scaling": "strong",
                                           "ssim": float(parallel.mean_from_partials(float(sums.item()), W16, W16)),
                                           "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce of 1 double per step"}
+    if world > 1:
+        # same strips, the cross-GPU sum fused into the reduction kernel: every rank's kernel stores its strip sum into every
+        # peer's exchange buffer over NVLink and adds up what lands in its own (ssim_cuda_compute_strip_allreduce); the
+        # buffers of the other processes are mapped through CUDA IPC handles
+        buf, handle = api.exchange_create(local)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        peers = [buf if r == rank else api.exchange_open(local, handles[r]) for r in range(world)]
+        allsum = torch.zeros(1, dtype=torch.float64, device=dev)
+        allval = torch.zeros(1, dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        epoch = [0]
+
+        def strips_p2p():
+            epoch[0] += 1
+            api.compute_strip_allreduce(local, sh, W16, s1 - s0, oy, orows, W16, a.data_ptr(), W16, b.data_ptr(), W16, m.data_ptr(), W16,
+                                        peers, rank, epoch[0], allsum.data_ptr(), allval.data_ptr(), status.data_ptr())
+
+        ms2 = timed(strips_p2p, 10)
+        torch.cuda.synchronize()
+        out["16384x16384_strips_with_map_peer_memory"] = {"ms": round(ms2, 4), "mpix_per_s": round(W16 * W16 / ms2 / 1e3, 1), "scaling": "strong",
+                                                          "ssim": float(allval.item()), "status": int(status.item()),
+                                                          "collective": "strip sums exchanged by NVLink peer stores inside the reduction kernel (no NCCL call)"}
+        dist.barrier()
     del a, b, m
 
     # configs[4]: 4096 x 1080p pairs with maps, 512 per GPU (weak scaling; fewer per GPU when more than 8 ranks are not available)

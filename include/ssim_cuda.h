@@ -136,6 +136,34 @@ int ssim_cuda_compute_strips(int nDevices, const int* devices, uint32_t width, u
                              float* map, ptrdiff_t mapStep, ptrdiff_t mapStride,
                              float* ssim);
 
+/*
+ * Strips of one image across GPUs with the cross-GPU sum fused into the reduction kernel: instead of an NCCL all-reduce after
+ * the launch (ssim_cuda_compute_strips, or torch.distributed in a one-process-per-GPU driver), the reduction kernel of every
+ * rank stores its strip sum straight into every peer's exchange buffer over NVLink (peer stores with release semantics at
+ * system scope), waits for the other ranks' sums to land in its own buffer and adds them in rank order: same result bits on
+ * every rank, no host round trip, no collective launch.  Replaces the same reference code as ssim_cuda_compute_strips().
+ *
+ *   exchange_create   allocates this rank's exchange buffer; ipcHandle64 (64 bytes, may be NULL) receives a handle that other
+ *                     PROCESSES pass to exchange_open(); threads of one process may use the returned pointer directly after
+ *                     exchange_enable_peer(device, ownerDevice).
+ *   compute_strip_allreduce   like ssim_cuda_compute_device() for ONE strip (frames = 1) of an image of `imageRows` rows:
+ *                     peerBufs[r] = rank r's exchange buffer as seen from this device (own buffer at [rank]); epoch = 1, 2, 3...
+ *                     the same on every rank for the same image; dSumAll/dSsimAll receive the sum over all strips and
+ *                     float(sum / double(uint32(width*imageRows))); *dStatus = 1 (and the results NaN) if a peer did not
+ *                     show up within SSIM_CUDA_EXCHANGE_TIMEOUT_MS (default 2000) -- the kernel never spins forever.
+ */
+int ssim_cuda_exchange_create(int device, void** dBuf, void* ipcHandle64);
+int ssim_cuda_exchange_open(int device, const void* ipcHandle64, void** dPeerBuf);
+int ssim_cuda_exchange_close(int device, void* dPeerBuf);
+int ssim_cuda_exchange_destroy(int device, void* dBuf);
+int ssim_cuda_exchange_enable_peer(int device, int peerDevice);
+int ssim_cuda_compute_strip_allreduce(int device, void* stream,
+                                      uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t imageRows,
+                                      const uint8_t* dA, size_t pitchA, const uint8_t* dB, size_t pitchB,
+                                      float* dMap, size_t mapPitch,
+                                      void* const* peerBufs, int world, int rank, uint64_t epoch,
+                                      double* dSumAll, float* dSsimAll, int* dStatus);
+
 /* Fills device planes with rows y0..y0+rows-1 of synthetic frame `frame` (ssim_b200/csrc/synth.h). */
 int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, uint8_t* dB, size_t pitchB,
                          uint32_t width, uint32_t rows, uint32_t y0, uint32_t frame, uint64_t seed);

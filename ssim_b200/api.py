@@ -57,6 +57,20 @@ def cuda_lib():
     lib.ssim_cuda_compute_u16.restype = C.c_int
     lib.ssim_cuda_compute_device_u16.argtypes = lib.ssim_cuda_compute_device.argtypes
     lib.ssim_cuda_compute_device_u16.restype = C.c_int
+    lib.ssim_cuda_exchange_create.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.ssim_cuda_exchange_create.restype = C.c_int
+    lib.ssim_cuda_exchange_open.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.ssim_cuda_exchange_open.restype = C.c_int
+    lib.ssim_cuda_exchange_close.argtypes = [C.c_int, C.c_void_p]
+    lib.ssim_cuda_exchange_close.restype = C.c_int
+    lib.ssim_cuda_exchange_destroy.argtypes = [C.c_int, C.c_void_p]
+    lib.ssim_cuda_exchange_destroy.restype = C.c_int
+    lib.ssim_cuda_exchange_enable_peer.argtypes = [C.c_int, C.c_int]
+    lib.ssim_cuda_exchange_enable_peer.restype = C.c_int
+    lib.ssim_cuda_compute_strip_allreduce.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                      u8p, C.c_size_t, u8p, C.c_size_t, f32p, C.c_size_t,
+                                                      C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint64, f64p, f32p, vp]
+    lib.ssim_cuda_compute_strip_allreduce.restype = C.c_int
     lib.ssim_cuda_last_launch_count.restype = C.c_int
     lib.ssim_cuda_compute_strips.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, u8p, C.c_ssize_t, C.c_ssize_t,
                                              u8p, C.c_ssize_t, C.c_ssize_t, f32p, C.c_ssize_t, C.c_ssize_t, C.POINTER(C.c_float)]
@@ -143,6 +157,30 @@ def compute_u16(a, b, want_map=False, want_ssim=True, width=None, height=None, s
                                            b.ctypes.data + 2 * b_off, step_b, stride_b,
                                            m.ctypes.data if want_map else None, 1, width, C.byref(out) if want_ssim else None))
     return (np.float32(out.value) if want_ssim else None), m
+
+
+def exchange_create(device):
+    """Allocates this rank's exchange buffer; returns (device pointer, 64-byte IPC handle)."""
+    buf = C.c_void_p()
+    handle = (C.c_ubyte * 64)()
+    _check(cuda_lib().ssim_cuda_exchange_create(device, C.byref(buf), handle))
+    return buf.value, bytes(handle)
+
+
+def exchange_open(device, handle):
+    """Maps another process's exchange buffer (IPC handle from exchange_create) into this process."""
+    buf = C.c_void_p()
+    raw = (C.c_ubyte * 64).from_buffer_copy(handle)
+    _check(cuda_lib().ssim_cuda_exchange_open(device, raw, C.byref(buf)))
+    return buf.value
+
+
+def compute_strip_allreduce(device, stream, width, src_rows, out_y0, out_rows, image_rows, d_a, pitch_a, d_b, pitch_b, d_map, map_pitch,
+                            peer_bufs, rank, epoch, d_sum_all, d_ssim_all=None, d_status=None):
+    """ssim_cuda_compute_strip_allreduce(): one strip, sum over ranks exchanged through peer memory inside the reduction kernel."""
+    arr = (C.c_void_p * len(peer_bufs))(*peer_bufs)
+    _check(cuda_lib().ssim_cuda_compute_strip_allreduce(device, stream, width, src_rows, out_y0, out_rows, image_rows, d_a, pitch_a, d_b, pitch_b,
+                                                       d_map, map_pitch, arr, len(peer_bufs), rank, epoch, d_sum_all, d_ssim_all, d_status))
 
 
 def compute_strips(devices, a, b, want_map=False):

@@ -347,12 +347,12 @@ long long plan_items(const Context* c, uint32_t width, uint32_t outRows, uint32_
 int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
                         uint32_t frames, const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB,
                         size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim,
-                        const ChunkPlan* chunk = nullptr, int elemBytes = 1)
+                        const ChunkPlan* chunk = nullptr, int elemBytes = 1, const ssimk::ExchangeParams* xchg = nullptr)
 {
     g_lastLaunches = 0;
     if (width == 0 || srcRows == 0 || outRows == 0 || frames == 0) return fail(EINVAL, "width, rows and frames must be non-zero");
     if (dA == nullptr || dB == nullptr) return fail(EINVAL, "dA or dB is NULL");
-    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr && chunk == nullptr) return fail(EINVAL, "no output requested");
+    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr && chunk == nullptr && xchg == nullptr) return fail(EINVAL, "no output requested");
     if ((uint64_t)outY0 + outRows > srcRows) return fail(EINVAL, "output rows [%u,%u) exceed the %u source rows", outY0, outY0 + outRows, srcRows);
     if (width > 0x7fffff00u || srcRows > 0x7fffff00u) return fail(EINVAL, "dimensions too large");
     if (((uintptr_t)dA | (uintptr_t)dB | pitchA | pitchB) & 15) return fail(EINVAL, "plane base addresses and pitches must be multiples of 16 bytes");
@@ -409,12 +409,13 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     CU_TRY(ssimk::launch_fused(stream, tm[0], tm[1], p));
     g_lastLaunches = 1;
 
-    if (!chunk && (dSums || dSsim)) {
+    if (!chunk && (dSums || dSsim || xchg)) {
         ssimk::FinalizeParams f;
         f.partials = partials; f.sums = dSums; f.ssim = dSsim;
         f.itemsPerFrame = (int)itemsPerFrame;
         f.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
-        CU_TRY(ssimk::launch_finalize(stream, f, (int)frames));
+        if (xchg) CU_TRY(ssimk::launch_finalize_allreduce(stream, f, *xchg));     // one strip: reduction + cross-GPU sum in one kernel
+        else      CU_TRY(ssimk::launch_finalize(stream, f, (int)frames));
         g_lastLaunches = 2;
     }
     return 0;
@@ -957,6 +958,92 @@ int ssim_cuda_compute_device_u16(int device, void* stream, uint32_t width, uint3
     CU_TRY(cudaSetDevice(device));
     return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, frames, (const uint8_t*)dA, pitchA, frameStrideA,
                                (const uint8_t*)dB, pitchB, frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim, nullptr, 2);
+}
+
+// ---- strip sums exchanged over peer memory (NVLink) inside the reduction kernel
+int ssim_cuda_exchange_create(int device, void** dBuf, void* ipcHandle64)
+{
+    if (!dBuf) return fail(EINVAL, "dBuf is NULL");
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    const size_t bytes = 2 * ssimk::kMaxRanks * sizeof(ssimk::ExchangeSlot);
+    CU_TRY(cudaMalloc(dBuf, bytes));
+    CU_TRY(cudaMemset(*dBuf, 0, bytes));
+    CU_TRY(cudaDeviceSynchronize());
+    if (ipcHandle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CU_TRY(cudaIpcGetMemHandle(&h, *dBuf));
+        memcpy(ipcHandle64, &h, sizeof(h));
+    }
+    return 0;
+}
+
+int ssim_cuda_exchange_open(int device, const void* ipcHandle64, void** dPeerBuf)
+{
+    if (!ipcHandle64 || !dPeerBuf) return fail(EINVAL, "handle or output pointer is NULL");
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipcHandle64, sizeof(h));
+    CU_TRY(cudaIpcOpenMemHandle(dPeerBuf, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int ssim_cuda_exchange_close(int device, void* dPeerBuf)
+{
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaIpcCloseMemHandle(dPeerBuf));
+    return 0;
+}
+
+int ssim_cuda_exchange_destroy(int device, void* dBuf)
+{
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFree(dBuf));
+    return 0;
+}
+
+int ssim_cuda_exchange_enable_peer(int device, int peerDevice)
+{
+    if (device == peerDevice) return 0;
+    CU_TRY(cudaSetDevice(device));
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peerDevice));
+    if (!can) return fail(ENODEV, "device %d cannot access device %d", device, peerDevice);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    CU_TRY(e);
+    return 0;
+}
+
+int ssim_cuda_compute_strip_allreduce(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
+                                      uint32_t imageRows, const uint8_t* dA, size_t pitchA, const uint8_t* dB, size_t pitchB,
+                                      float* dMap, size_t mapPitch, void* const* peerBufs, int world, int rank, uint64_t epoch,
+                                      double* dSumAll, float* dSsimAll, int* dStatus)
+{
+    if (!peerBufs || !dSumAll) return fail(EINVAL, "peerBufs or dSumAll is NULL");
+    if (world < 1 || world > ssimk::kMaxRanks || rank < 0 || rank >= world) return fail(EINVAL, "world %d / rank %d out of range (max %d ranks)", world, rank, ssimk::kMaxRanks);
+    if (epoch == 0) return fail(EINVAL, "epoch must be >= 1");
+    for (int r = 0; r < world; ++r) if (!peerBufs[r]) return fail(EINVAL, "peerBufs[%d] is NULL", r);
+    Context* c;
+    int rc = get_context(device, &c);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(device));
+    ssimk::ExchangeParams x;
+    memset(&x, 0, sizeof(x));
+    for (int r = 0; r < world; ++r) x.peers[r] = (ssimk::ExchangeSlot*)peerBufs[r];
+    x.world = world; x.rank = rank; x.epoch = epoch;
+    static const unsigned long long timeoutMs = [] { const char* e = getenv("SSIM_CUDA_EXCHANGE_TIMEOUT_MS"); return e ? (unsigned long long)atoll(e) : 2000ull; }();
+    x.timeoutNs = timeoutMs * 1000000ull;
+    x.sumAll = dSumAll; x.ssimAll = dSsimAll; x.status = dStatus;
+    x.invCountAll = 1.0 / (double)(uint32_t)(width * imageRows);       // uint32 product, as src/ssim.cpp:1102
+    return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, 1, dA, pitchA, 0, dB, pitchB, 0, dMap, mapPitch, 0,
+                               nullptr, nullptr, nullptr, 1, &x);
 }
 
 int ssim_cuda_last_launch_count(void) { return g_lastLaunches; }

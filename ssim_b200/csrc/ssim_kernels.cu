@@ -526,6 +526,56 @@ __global__ void __launch_bounds__(256) ssim_finalize_kernel(const FinalizeParams
 }
 
 // ------------------------------------------------------------------------------------------------ layout helpers
+// Reduction of ONE strip + all-reduce of the strip sums over peer memory, in one kernel (see ExchangeParams).
+__global__ void __launch_bounds__(256) ssim_finalize_allreduce_kernel(const FinalizeParams p, const ExchangeParams x)
+{
+    __shared__ double sh[256];
+    __shared__ double vals[kMaxRanks];
+    __shared__ int failed;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < p.itemsPerFrame; i += 256) acc += p.partials[i];
+    sh[threadIdx.x] = acc;
+    if (threadIdx.x == 0) failed = 0;
+    __syncthreads();
+    #pragma unroll
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    const unsigned half = (unsigned)(x.epoch & 1ull) * kMaxRanks;
+    if ((int)threadIdx.x < x.world) {
+        // one thread per peer: value, then the epoch with release semantics at system scope
+        ExchangeSlot* dst = x.peers[threadIdx.x] + half + x.rank;
+        dst->value = sh[0];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(&dst->epoch), "l"(x.epoch) : "memory");
+    }
+    if (threadIdx.x == 0) {
+        if (p.sums) p.sums[0] = sh[0];
+        if (p.ssim) p.ssim[0] = (float)(sh[0] * p.invCount);
+    }
+    if ((int)threadIdx.x < x.world) {
+        const ExchangeSlot* src = x.peers[x.rank] + half + threadIdx.x;
+        unsigned long long t0, now, seen;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&src->epoch) : "memory");
+            if (seen == x.epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > x.timeoutNs) { failed = 1; break; }
+        }
+        vals[threadIdx.x] = src->value;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int r = 0; r < x.world; ++r) total += vals[r];
+        if (failed) total = __longlong_as_double(0x7ff8000000000000ll);
+        *x.sumAll = total;
+        if (x.ssimAll) *x.ssimAll = (float)(total * x.invCountAll);
+        if (x.status) *x.status = failed;
+    }
+}
+
 // gathers one channel of an arbitrarily strided u8 image into a dense pitched plane (the canonical input of the
 // fused kernel); replaces the addressing part of retrieve_tile (src/ssim.cpp:531-548) for step != 1 / negative strides.
 __global__ void pack_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, const uint8_t* __restrict__ src,
@@ -632,6 +682,12 @@ cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUte
 cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames)
 {
     ssim_finalize_kernel<<<frames, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_allreduce(cudaStream_t stream, const FinalizeParams& p, const ExchangeParams& x)
+{
+    ssim_finalize_allreduce_kernel<<<1, 256, 0, stream>>>(p, x);
     return cudaGetLastError();
 }
 

@@ -89,6 +89,24 @@ struct FinalizeParams {
     double invCount;         // 1 / double(uint32(width*outRows))
 };
 
+// Cross-GPU sum fused into the reduction kernel (strips of one image): every rank owns an exchange buffer of
+// 2 x kMaxRanks slots; the reduction kernel of rank r stores its partial sum straight into slot [epoch & 1][r] of EVERY
+// peer's buffer (NVLink peer stores, value then epoch with release semantics at system scope), then waits until its own
+// buffer holds all `world` slots of this epoch and adds them up in rank order (deterministic, identical on every rank).
+constexpr int kMaxRanks = 16;
+struct ExchangeSlot { double value; unsigned long long epoch; };
+struct ExchangeParams {
+    ExchangeSlot* peers[kMaxRanks];   // device pointers to every rank's exchange buffer (own one at [rank])
+    int world, rank;
+    unsigned long long epoch;         // >= 1, same sequence on every rank; parity selects the half of the buffer
+    unsigned long long timeoutNs;     // give up waiting after this long (status = 1, result NaN) instead of hanging the GPU
+    double* sumAll;                   // out: sum over ranks
+    float*  ssimAll;                  // out (may be NULL): float(sumAll * invCountAll)
+    double invCountAll;
+    int* status;                      // out: 0 ok, 1 timed out
+};
+cudaError_t launch_finalize_allreduce(cudaStream_t stream, const FinalizeParams& p, const ExchangeParams& x);
+
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p);
 cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames);
 // per-device preparation (sets the dynamic shared-memory limit on the CURRENT device) + kernel facts

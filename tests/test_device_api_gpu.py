@@ -216,3 +216,52 @@ def test_full_size_known_answers(golden):
     torch.cuda.synchronize()
     for i, f in enumerate(frames):
         assert abs(float(fv[i].item()) - golden["synthetic"]["1920x1080_f%d" % f]["ref_f64_auto"]) <= GLOBAL_TOL
+
+
+def test_strip_sums_exchanged_through_peer_memory():
+    """ssim_cuda_compute_strip_allreduce(): the reduction kernel of every rank stores its strip sum into every peer's exchange
+    buffer and adds up what lands in its own.  One process drives all visible GPUs (ranks = devices; with a single GPU the
+    ranks share device 0, which still exercises the slot / epoch protocol); every rank must end with the bits of the full-image
+    result, twice in a row (epoch parity), and a missing peer must time out instead of hanging."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    world = 4
+    W, H = 640, 333
+    a, b = synth_pair(W, H, 2)
+    o, osum, _ = oracle.oracle_ssim(a, b)
+    devs = [r % n_dev for r in range(world)]
+    lib = api.cuda_lib()
+    bufs = [api.exchange_create(d)[0] for d in devs]
+    for d in set(devs):
+        for e in set(devs):
+            assert lib.ssim_cuda_exchange_enable_peer(d, e) == 0
+    state = []
+    for r in range(world):
+        s0, s1, oy, orows = parallel.strip_bounds(H, world, r)
+        dev = torch.device("cuda", devs[r])
+        da = torch.from_numpy(np.ascontiguousarray(a[s0:s1])).to(dev); db = torch.from_numpy(np.ascontiguousarray(b[s0:s1])).to(dev)
+        state.append((da, db, s1 - s0, oy, orows, torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.float32, device=dev),
+                      torch.full((1,), -1, dtype=torch.int32, device=dev), torch.cuda.Stream(device=dev)))
+    for epoch in (1, 2, 3):
+        for r in range(world):
+            da, db, rows, oy, orows, dsum, dval, dst, st = state[r]
+            api.compute_strip_allreduce(devs[r], st.cuda_stream, W, rows, oy, orows, H, da.data_ptr(), W, db.data_ptr(), W, None, 0,
+                                        bufs, r, epoch, dsum.data_ptr(), dval.data_ptr(), dst.data_ptr())
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        vals = [float(s[6].item()) for s in state]
+        sums = [float(s[5].item()) for s in state]
+        assert all(int(s[7].item()) == 0 for s in state)
+        assert len(set(sums)) == 1 and len(set(vals)) == 1                      # identical bits on every rank
+        assert abs(vals[0] - float(o)) <= GLOBAL_TOL and abs(sums[0] - osum) <= 2e-7 * W * H
+    # a rank whose peers never arrive gives up after the time-out (status 1, NaN), it does not hang
+    import os
+    da, db, rows, oy, orows, dsum, dval, dst, st = state[0]
+    lonely = [api.exchange_create(devs[0])[0] for _ in range(2)]
+    os.environ["SSIM_CUDA_EXCHANGE_TIMEOUT_MS"] = "2000"
+    api.compute_strip_allreduce(devs[0], st.cuda_stream, W, rows, oy, orows, H, da.data_ptr(), W, db.data_ptr(), W, None, 0,
+                                lonely, 0, 1, dsum.data_ptr(), dval.data_ptr(), dst.data_ptr())
+    torch.cuda.synchronize(devs[0])
+    assert int(dst.item()) == 1 and np.isnan(float(dsum.item()))
+    for bptr, d in zip(bufs + lonely, devs + [devs[0]] * 2):
+        assert lib.ssim_cuda_exchange_destroy(d, bptr) == 0
