@@ -480,6 +480,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_proxy_async();
     }
     __syncthreads();                                                    // the only CTA-wide barrier
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       // the reduction grid may be set up from now on (it waits for our completion)
 
     const uint32_t item = blockIdx.x * kPairsPerCta + pair;           // < 2^31, checked by the host
     const uint32_t pairSmem = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + pair * PixGeo<kU16>::kPairSmemBytes;
@@ -508,6 +509,9 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 __global__ void __launch_bounds__(256) ssim_finalize_kernel(const FinalizeParams p)
 {
     __shared__ double sh[256];
+    // launched with programmatic stream serialization: this grid may start while the fused kernel is still draining; it
+    // must not read the partial sums before that kernel has completed and flushed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int frame = blockIdx.x;
     const double* src = p.partials + (long long)frame * p.itemsPerFrame;
     double acc = 0.0;
@@ -532,6 +536,7 @@ __global__ void __launch_bounds__(256) ssim_finalize_allreduce_kernel(const Fina
     __shared__ double sh[256];
     __shared__ double vals[kMaxRanks];
     __shared__ int failed;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // see ssim_finalize_kernel
     double acc = 0.0;
     for (int i = threadIdx.x; i < p.itemsPerFrame; i += 256) acc += p.partials[i];
     sh[threadIdx.x] = acc;
@@ -681,14 +686,25 @@ cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUte
 
 cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames)
 {
-    ssim_finalize_kernel<<<frames, 256, 0, stream>>>(p);
-    return cudaGetLastError();
+    // programmatic dependent launch: the reduction grid is set up while the fused kernel's last CTAs are still running
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(frames); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ssim_finalize_kernel, p);
 }
 
 cudaError_t launch_finalize_allreduce(cudaStream_t stream, const FinalizeParams& p, const ExchangeParams& x)
 {
-    ssim_finalize_allreduce_kernel<<<1, 256, 0, stream>>>(p, x);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ssim_finalize_allreduce_kernel, p, x);
 }
 
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm)
