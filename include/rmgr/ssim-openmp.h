@@ -27,7 +27,7 @@ inline int32_t compute_ssim_openmp(float* ssim, const GeneralParams& params) RMG
     return ::rmgr_ssim_compute_ssim_openmp(ssim, &params);
 }
 
-RMGR_DEPRECATED_MSG("Use compute_ssim_openmp(float* ssim, const GeneralParams& params) instead")
+RMGR_DEPRECATED_MSG("deprecated overload: call compute_ssim_openmp(&ssim, generalParams) and test its return code")
 inline float compute_ssim_openmp(const UnthreadedParams& params) RMGR_NOEXCEPT
 {
     float ssim;

@@ -200,10 +200,10 @@ struct Params: public rmgr_ssim_Params_
 };
 
 /* Returns the SSIM, or float(-errno) on error                                  (reference ssim.h:713) */
-RMGR_DEPRECATED_MSG("Use compute_ssim(float* ssim, const GeneralParams& params, const ThreadPool* threadPool) instead")
+RMGR_DEPRECATED_MSG("deprecated overload: call compute_ssim(&ssim, generalParams, threadPool) and test its return code")
 float compute_ssim(const Params& params) RMGR_NOEXCEPT;
 
-RMGR_DEPRECATED_MSG("You don't need this if you use compute_ssim(float* ssim, const GeneralParams& params, const ThreadPool* threadPool)")
+RMGR_DEPRECATED_MSG("only meaningful with the deprecated float compute_ssim(const Params&): the new overload returns the error code itself")
 inline int32_t get_errno(float ssim) RMGR_NOEXCEPT                              /* reference ssim.h:725 */
 {
     return (ssim>=0) ? 0 : -int32_t(ssim);

@@ -12,26 +12,40 @@
 
 #include "ssim_cuda.h"
 
-#ifndef RMGR_SSIM_REPORT_ERROR
-    #ifndef NDEBUG
-        #define RMGR_SSIM_REPORT_ERROR(...)  fprintf(stderr, __VA_ARGS__)
-    #else
-        #define RMGR_SSIM_REPORT_ERROR(...)
-    #endif
+// Diagnostics go to stderr in debug builds only, through the same user-overridable macro name as the reference
+// (src/ssim.cpp:37-43), so a project that already redirects RMGR_SSIM_REPORT_ERROR keeps doing so.
+#if !defined(RMGR_SSIM_REPORT_ERROR)
+#   if defined(NDEBUG)
+#       define RMGR_SSIM_REPORT_ERROR(...) ((void)0)
+#   else
+#       define RMGR_SSIM_REPORT_ERROR(...) std::fprintf(stderr, __VA_ARGS__)
+#   endif
 #endif
 
 namespace
 {
 
-void* default_alloc(size_t size, size_t alignment) RMGR_NOEXCEPT
+// rejects a call with EINVAL and says why (debug builds)
+rmgr_int32_t reject(const char* what) RMGR_NOEXCEPT
 {
-    void* address = NULL;
-    return (::posix_memalign(&address, alignment, size) == 0) ? address : NULL;
+    RMGR_SSIM_REPORT_ERROR("rmgr-ssim (CUDA): invalid argument: %s\n", what);
+    (void)what;
+    return EINVAL;
 }
 
-void default_dealloc(void* address) RMGR_NOEXCEPT
+// The allocation hooks are part of the reference's Params; the GPU build accepts them and never calls them (scratch is
+// device memory), but use_default_allocator() still has to install a working pair (src/ssim.cpp:206-217).
+void* aligned_new(size_t bytes, size_t alignment) RMGR_NOEXCEPT
 {
-    ::free(address);
+    void* p = NULL;
+    if (::posix_memalign(&p, alignment, bytes) != 0)
+        p = NULL;
+    return p;
+}
+
+void aligned_delete(void* p) RMGR_NOEXCEPT
+{
+    ::free(p);
 }
 
 // SSIM_CUDA_DEVICE selects the GPU used by the drop-in API (default 0)
@@ -44,62 +58,56 @@ int selected_device() RMGR_NOEXCEPT
     return device;
 }
 
+// one image description = pointer to pixel (0,0), byte distance between pixels, byte distance between rows
+void describe(rmgr_ssim_ImgParams& img, const rmgr_uint8_t* origin, ptrdiff_t step, ptrdiff_t stride) RMGR_NOEXCEPT
+{
+    img.topLeft = origin;
+    img.step    = step;
+    img.stride  = stride;
+}
+
 } // namespace
 
 
+// channel `channelNum` of an interleaved image (reference src/ssim.cpp:156-178)
 extern "C" rmgr_int32_t rmgr_ssim_init_interleaved(rmgr_ssim_ImgParams* params, const rmgr_uint8_t* data, ptrdiff_t imgStride, rmgr_uint32_t channelCount, rmgr_uint32_t channelNum) RMGR_NOEXCEPT
 {
-    if (params == NULL || data == NULL || channelNum >= channelCount)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: params/data cannot be NULL and channelNum must be < channelCount\n");
-        return EINVAL;
-    }
-    params->topLeft = data + channelNum;
-    params->step    = ptrdiff_t(channelCount);
-    params->stride  = imgStride;
+    if (!params || !data)
+        return reject("init_interleaved: params and data must not be NULL");
+    if (channelNum >= channelCount)
+        return reject("init_interleaved: channelNum must be below channelCount");
+    describe(*params, data + channelNum, (ptrdiff_t)channelCount, imgStride);
     return 0;
 }
 
 
+// plane `planeNum` of a planar image (reference src/ssim.cpp:181-203)
 extern "C" rmgr_int32_t rmgr_ssim_init_planar(rmgr_ssim_ImgParams* params, rmgr_uint8_t const* const planes[], const ptrdiff_t strides[], rmgr_uint32_t planeNum) RMGR_NOEXCEPT
 {
-    if (params == NULL || planes == NULL || planes[planeNum] == NULL || strides == NULL)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: params, planes, planes[planeNum] and strides cannot be NULL\n");
-        return EINVAL;
-    }
-    params->topLeft = planes[planeNum];
-    params->step    = 1;
-    params->stride  = strides[planeNum];
+    if (!params || !planes || !strides || !planes[planeNum])
+        return reject("init_planar: params, planes, strides and the selected plane must not be NULL");
+    describe(*params, planes[planeNum], 1, strides[planeNum]);
     return 0;
 }
 
 
 extern "C" rmgr_int32_t rmgr_ssim_use_default_allocator(rmgr_ssim_Params* params) RMGR_NOEXCEPT
 {
-    if (params == NULL)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: params cannot be NULL\n");
-        return EINVAL;
-    }
-    params->alloc   = default_alloc;
-    params->dealloc = default_dealloc;
+    if (!params)
+        return reject("use_default_allocator: params must not be NULL");
+    params->alloc   = aligned_new;
+    params->dealloc = aligned_delete;
     return 0;
 }
 
 
 extern "C" rmgr_int32_t rmgr_ssim_get_version(rmgr_ssim_Version* version) RMGR_NOEXCEPT
 {
-    static const char versionString[] = RMGR_SSIM_VERSION_STRING;
-    if (version == NULL)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: version cannot be NULL\n");
-        return EINVAL;
-    }
-    version->major  = RMGR_SSIM_VERSION_MAJOR;
-    version->minor  = RMGR_SSIM_VERSION_MINOR;
-    version->patch  = RMGR_SSIM_VERSION_PATCH;
-    version->string = versionString;
+    static const char text[] = RMGR_SSIM_VERSION_STRING;
+    if (!version)
+        return reject("get_version: version must not be NULL");
+    const rmgr_ssim_Version v = {RMGR_SSIM_VERSION_MAJOR, RMGR_SSIM_VERSION_MINOR, RMGR_SSIM_VERSION_PATCH, text};
+    *version = v;
     return 0;
 }
 
@@ -109,53 +117,39 @@ namespace rmgr { namespace ssim
 
 int32_t compute_ssim(float* ssim, const GeneralParams& params, const ThreadPool* threadPool) RMGR_NOEXCEPT
 {
-    // Same checks, same order as the reference (src/ssim.cpp:962-978)
-    if (ssim == NULL && params.ssimMap == NULL)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameters: both ssim and ssimMap are NULL, nothing will be computed\n");
-        return EINVAL;
-    }
-    if (params.imgA.topLeft == NULL || params.imgB.topLeft == NULL)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: imgA.topLeft or imgB.topLeft is NULL\n");
-        return EINVAL;
-    }
-    if (threadPool != NULL && threadPool->dispatch != NULL && threadPool->threadCount == 0u)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: threadCount cannot be 0 if threadPool is not NULL\n");
-        return EINVAL;
-    }
+    // Same checks in the same order as the reference (src/ssim.cpp:962-978), so a caller sees the same errno for a
+    // call that is wrong in several ways at once.
+    const bool wantsMap = params.ssimMap != NULL;
+    if (!ssim && !wantsMap)
+        return reject("compute_ssim: neither a global result nor a map was requested");
+    if (!params.imgA.topLeft || !params.imgB.topLeft)
+        return reject("compute_ssim: an image pointer is NULL");
+    if (threadPool && threadPool->dispatch && threadPool->threadCount == 0)
+        return reject("compute_ssim: a thread pool with a dispatch function needs threadCount > 0");
     // Divergence (documented in the header): the reference returns garbage for empty images
     if (params.width == 0 || params.height == 0)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: width and height cannot be 0\n");
-        return EINVAL;
-    }
+        return reject("compute_ssim: width and height must be non-zero");
 
     // With no map, ssimStep/ssimStride are ignored (src/ssim.cpp:980-987).  The thread pool and the allocation
     // hooks are not used: tiles are scheduled on the GPU grid and scratch lives in device memory.
-    const int32_t result = ::ssim_cuda_compute(selected_device(), params.width, params.height,
-                                               params.imgA.topLeft, params.imgA.step, params.imgA.stride,
-                                               params.imgB.topLeft, params.imgB.step, params.imgB.stride,
-                                               params.ssimMap, params.ssimMap ? params.ssimStep : 0, params.ssimMap ? params.ssimStride : 0,
-                                               ssim);
-    if (result != 0)
-        RMGR_SSIM_REPORT_ERROR("ssim_cuda: %s\n", ::ssim_cuda_last_error_string());
-    return result;
+    const int32_t rc = ::ssim_cuda_compute(selected_device(), params.width, params.height,
+                                           params.imgA.topLeft, params.imgA.step, params.imgA.stride,
+                                           params.imgB.topLeft, params.imgB.step, params.imgB.stride,
+                                           params.ssimMap, wantsMap ? params.ssimStep : 0, wantsMap ? params.ssimStride : 0,
+                                           ssim);
+    if (rc != 0)
+        RMGR_SSIM_REPORT_ERROR("rmgr-ssim (CUDA): %s\n", ::ssim_cuda_last_error_string());
+    return rc;
 }
 
 
+// deprecated overload: threaded parameters in one struct, result or -errno as a float (src/ssim.cpp:1109-1120)
 float compute_ssim(const Params& params) RMGR_NOEXCEPT
 {
-    // src/ssim.cpp:1109-1120
-    ThreadPool threadPool;
-    threadPool.dispatch    = params.threadPool;
-    threadPool.context     = params.threadPoolContext;
-    threadPool.threadCount = params.threadCount;
-
-    float ssim = 0.0f;
-    const int32_t result = compute_ssim(&ssim, params, &threadPool);
-    return (result == 0) ? ssim : float(-result);
+    const ThreadPool pool = {params.threadPool, params.threadPoolContext, params.threadCount};
+    float value = 0.0f;
+    const int32_t rc = compute_ssim(&value, params, &pool);
+    return rc ? -float(rc) : value;
 }
 
 }} // namespace rmgr::ssim
@@ -163,11 +157,8 @@ float compute_ssim(const Params& params) RMGR_NOEXCEPT
 
 extern "C" rmgr_int32_t rmgr_ssim_compute_ssim(float* ssim, const rmgr_ssim_Params* params, const rmgr_ssim_ThreadPool* threadPool) RMGR_NOEXCEPT
 {
-    if (params == NULL)
-    {
-        RMGR_SSIM_REPORT_ERROR("Invalid parameter: params cannot be NULL\n");
-        return EINVAL;
-    }
+    if (!params)
+        return reject("compute_ssim: params must not be NULL");
     return rmgr::ssim::compute_ssim(ssim, *params, threadPool);
 }
 
