@@ -280,39 +280,7 @@ int acquire_host_context(Context** c, std::unique_lock<std::mutex>* lock)
 // 4K image only has 60 bands, so segments must also be numerous enough to occupy ctasPerSm*4 warps on every SM.
 void choose_segments(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, int* segRows, int* segs)
 {
-    const long long bands = (width + ssimk::kBandW - 1) / ssimk::kBandW;
-    const long long units = bands * frames;
-    long long s;
-    if (g_segRowsOverride > 0) {
-        s = (outRows + g_segRowsOverride - 1) / g_segRowsOverride;
-    } else {
-        // The number of segments per frame decides both the halo overhead (10 extra input rows per segment) and how full
-        // the last wave of CTAs is.  Measured on B200 (tools/dev/batch_sweep.py, strip_sweep.py): 64 x 4K with 720-row
-        // segments = 9.73 waves 240.8k Mpix/s, 540-row = 12.97 waves 248.4k; a 16384 x 2058 strip with 515-row segments
-        // (0.86 waves) 187 us, 229-row (1.95 waves) 169 us.  Pick the count that minimises
-        //     waves x (rows + halo + per-item set-up),
-        // a last wave that fills at most half the CTA slots counting 0.4-0.7 (its CTAs have an SM to themselves and run
-        // faster); the candidates stop where a segment would drop below 24 rows.
-        const long long ctaSlots = (long long)c->numSMs * c->ctasPerSm;
-        const long long maxSegs = std::max<long long>(1, std::min<long long>(outRows / 24, 256));
-        double best = 0;
-        s = 1;
-        for (long long cand = 1; cand <= maxSegs; ++cand) {
-            const long long rows = (outRows + cand - 1) / cand;
-            const long long nseg = (outRows + rows - 1) / rows;
-            if (nseg != cand && cand != 1) continue;                    // same partition as a smaller candidate
-            const long long ctas = (units * nseg + ssimk::kPairsPerCta - 1) / ssimk::kPairsPerCta;
-            const long long full = ctas / ctaSlots, rem = ctas % ctaSlots;
-            double tail = 0.0;
-            if (rem > 0) tail = 2 * rem > ctaSlots ? 1.0 : 0.4 + 0.3 * (double)(2 * rem) / (double)ctaSlots;
-            const double cost = ((double)full + tail) * (double)(rows + 2 * ssimk::kHalo + 12);
-            if (cand == 1 || cost < best) { best = cost; s = cand; }
-        }
-    }
-    s = std::max<long long>(1, std::min<long long>(s, outRows));
-    int rows = (int)((outRows + s - 1) / s);
-    *segRows = rows;
-    *segs = (int)((outRows + rows - 1) / rows);
+    ssimk::plan_segments((long long)c->numSMs * c->ctasPerSm, width, outRows, frames, g_segRowsOverride, segRows, segs);
 }
 
 int get_partials(Context* c, cudaStream_t stream, size_t bytes, double** out)

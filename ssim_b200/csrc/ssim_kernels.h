@@ -81,6 +81,46 @@ inline void fast_div(uint32_t d, uint32_t* mul, uint32_t* shift)
     *shift = L - 1;
 }
 
+// Work partition (pure host logic, unit-tested on the CPU: tests/clients/plan_check.cpp).  A work item is (frame, row
+// segment, 64-column band).  The number of segments per frame decides both the halo overhead (10 extra input rows per
+// segment) and how full the last wave of CTAs is.  Measured on B200 (tools/dev/batch_sweep.py, strip_sweep.py): 64 x 4K
+// with 720-row segments = 9.73 waves 240.8k Mpix/s, 540-row = 12.97 waves 248.4k; a 16384 x 2058 strip with 515-row
+// segments (0.86 waves) 187 us, 229-row (1.95 waves) 169 us.  Pick the count that minimises
+//     waves x (rows + halo + per-item set-up),
+// a last wave that fills at most half the CTA slots counting 0.4-0.7 (its CTAs have an SM to themselves and run faster);
+// the candidates stop where a segment would drop below 24 rows.  overrideRows > 0 forces that many rows per segment.
+inline void plan_segments(long long ctaSlots, uint32_t width, uint32_t outRows, uint32_t frames, int overrideRows, int* segRows, int* segs)
+{
+    const long long bands = ((long long)width + kBandW - 1) / kBandW;
+    const long long units = bands * frames;
+    long long s = 1;
+    if (overrideRows > 0) {
+        s = ((long long)outRows + overrideRows - 1) / overrideRows;
+    } else {
+        long long maxSegs = outRows / 24;
+        if (maxSegs > 256) maxSegs = 256;
+        if (maxSegs < 1) maxSegs = 1;
+        if (ctaSlots < 1) ctaSlots = 1;
+        double best = 0;
+        for (long long cand = 1; cand <= maxSegs; ++cand) {
+            const long long rows = ((long long)outRows + cand - 1) / cand;
+            const long long nseg = ((long long)outRows + rows - 1) / rows;
+            if (nseg != cand && cand != 1) continue;                    // same partition as a smaller candidate
+            const long long ctas = (units * nseg + kPairsPerCta - 1) / kPairsPerCta;
+            const long long full = ctas / ctaSlots, rem = ctas % ctaSlots;
+            double tail = 0.0;
+            if (rem > 0) tail = 2 * rem > ctaSlots ? 1.0 : 0.4 + 0.3 * (double)(2 * rem) / (double)ctaSlots;
+            const double cost = ((double)full + tail) * (double)(rows + 2 * kHalo + 12);
+            if (cand == 1 || cost < best) { best = cost; s = cand; }
+        }
+    }
+    if (s > (long long)outRows) s = outRows;
+    if (s < 1) s = 1;
+    const int rows = (int)(((long long)outRows + s - 1) / s);
+    *segRows = rows;
+    *segs = (int)(((long long)outRows + rows - 1) / rows);
+}
+
 struct FinalizeParams {
     const double* partials;
     double* sums;            // may be NULL

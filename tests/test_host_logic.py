@@ -162,12 +162,14 @@ def test_two_rank_gloo_strips_and_batch(tmp_path):
         assert p.returncode == 0, o
 
 
-def test_fast_div_constants_are_exact(tmp_path):
-    """ssimk::fast_div() (host side of the kernel's work-item decode) against plain division, compiled as host C++."""
-    exe = str(tmp_path / "fast_div_check")
-    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "clients", "fast_div_check.cpp")
+@pytest.mark.parametrize("name", ["fast_div_check", "plan_check"])
+def test_host_side_kernel_helpers(tmp_path, name):
+    """Host-only logic that lives in ssim_kernels.h, compiled as plain C++: fast_div() (the kernel's work-item decode) against
+    plain division, plan_segments() (rows per work item) for coverage invariants and the documented choices."""
+    exe = str(tmp_path / name)
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "clients", name + ".cpp")
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ssim_b200", "csrc")
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", inc, "-I", "/usr/local/cuda/include", src, "-o", exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.startswith("fast_div ok"), r.stdout
+    assert r.returncode == 0 and " ok" in r.stdout, r.stdout
