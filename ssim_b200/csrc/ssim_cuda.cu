@@ -543,10 +543,12 @@ int finish_general(const GeneralJob& job)
 // up to 5 below its last output row, so its H2D covers 5 extra rows; everything lands in one full-height device plane and
 // the kernel addresses it with (srcRows = H, outY0, outRows), i.e. exactly the strip mechanism of the multi-GPU path.
 int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t strideA, const uint8_t* b, ptrdiff_t strideB,
-                      float* map, ptrdiff_t mapStride, float* ssim)
+                      float* map, ptrdiff_t mapStride, float* ssim, int elemBytes = 1)
 {
+    // a, b: byte pointers; strideA/strideB in BYTES; elemBytes = 1 (8-bit) or 2 (16-bit pixels)
     CU_TRY(cudaSetDevice(c->device));
-    const size_t pitch = align_up(W, 16), mapPitch = align_up(W, 4);
+    const size_t rowBytes = (size_t)W * elemBytes;
+    const size_t pitch = align_up(rowBytes, 16), mapPitch = align_up(W, 4);
     int rc;
     if ((rc = c->planeA.ensure(pitch * H)) || (rc = c->planeB.ensure(pitch * H))) return rc;
     if (map && (rc = c->map.ensure(mapPitch * H * sizeof(float)))) return rc;
@@ -554,7 +556,7 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
     // makes finer chunks lose, and graded chunk sizes (small first/last chunks to shorten pipeline fill and drain) measured
     // no better than 4 uniform chunks for a 4K pair (tools/dev/e2e_sweep.py).
     static const uint32_t chunkBytes = [] { const char* e = getenv("SSIM_CUDA_CHUNK_KB"); return (e ? (uint32_t)atoi(e) : 2048u) << 10; }();
-    const uint32_t targetRows = std::max<uint32_t>(64, chunkBytes / std::max<uint32_t>(W, 1));
+    const uint32_t targetRows = std::max<uint32_t>(64, chunkBytes / std::max<uint32_t>((uint32_t)rowBytes, 1));
     const int nChunks = std::max<int>(2, (int)std::min<uint32_t>(Context::kMaxChunks, (H + targetRows - 1) / targetRows));
     std::vector<uint32_t> bounds(nChunks + 1);                 // chunk k covers rows [bounds[k], bounds[k+1])
     for (int k = 0; k <= nChunks; ++k) bounds[k] = (uint32_t)((uint64_t)H * k / nChunks);
@@ -565,7 +567,8 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
 
     // tensor maps of the whole planes, encoded once; one partial-sum buffer for all chunks, one finalize at the end
     CUtensorMap maps[2];
-    if ((rc = make_plane_map(&maps[0], dA, W, H, 1, pitch, 0, ssimk::kLoadRows)) || (rc = make_plane_map(&maps[1], dB, W, H, 1, pitch, 0, ssimk::kLoadRows))) return rc;
+    if ((rc = make_plane_map(&maps[0], dA, W, H, 1, pitch, 0, ssimk::kLoadRows, elemBytes)) ||
+        (rc = make_plane_map(&maps[1], dB, W, H, 1, pitch, 0, ssimk::kLoadRows, elemBytes))) return rc;
     long long totalItems = 0;
     for (int k = 0; k < nChunks; ++k) {
         const uint32_t y0 = bounds[k], y1 = bounds[k + 1];
@@ -580,9 +583,9 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
         const uint32_t y0 = bounds[k], y1 = bounds[k + 1];
         const uint32_t need = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
         if (need > copied) {
-            CU_TRY(cudaMemcpy2DAsync(dA + (size_t)copied * pitch, pitch, a + (ptrdiff_t)copied * strideA, (size_t)strideA, W, need - copied,
+            CU_TRY(cudaMemcpy2DAsync(dA + (size_t)copied * pitch, pitch, a + (ptrdiff_t)copied * strideA, (size_t)strideA, rowBytes, need - copied,
                                      cudaMemcpyHostToDevice, c->streamIn));
-            CU_TRY(cudaMemcpy2DAsync(dB + (size_t)copied * pitch, pitch, b + (ptrdiff_t)copied * strideB, (size_t)strideB, W, need - copied,
+            CU_TRY(cudaMemcpy2DAsync(dB + (size_t)copied * pitch, pitch, b + (ptrdiff_t)copied * strideB, (size_t)strideB, rowBytes, need - copied,
                                      cudaMemcpyHostToDevice, c->streamIn));
             copied = need;
         }
@@ -593,7 +596,7 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
         long long items = 0;
         plan.maps = maps; plan.partials = partials + itemsDone; plan.itemsOut = &items;
         rc = compute_device_impl(c, c->stream, W, H, y0, y1 - y0, 1, dA, pitch, 0, dB, pitch, 0,
-                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, nullptr, nullptr, &plan);
+                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, nullptr, nullptr, &plan, elemBytes);
         if (rc) return rc;
         itemsDone += items;
         if (map) {
@@ -642,6 +645,12 @@ int compute_general_u16(Context* c, uint32_t W, uint32_t H, const uint16_t* a, p
 {
     std::unique_lock<std::mutex> lock;
     if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
+    // same pipelined path as 8-bit images for large plain-row host images (H2D / kernel / D2H overlapped in row chunks)
+    if ((uint64_t)W * H >= (1u << 20) && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
+        classify(a) == Where::Host && classify(b) == Where::Host &&
+        (map == nullptr || (mapStep == 1 && mapStride >= (ptrdiff_t)W && classify(map) == Where::Host)) &&
+        getenv("SSIM_CUDA_NO_PIPELINE") == nullptr)
+        return compute_pipelined(c, W, H, (const uint8_t*)a, 2 * strideA, (const uint8_t*)b, 2 * strideB, map, mapStride, ssim, 2);
     GeneralJob job;
     int rc = enqueue_general(c, W, H, 0, H, (const uint8_t*)a, 2 * stepA, 2 * strideA, (const uint8_t*)b, 2 * stepB, 2 * strideB, map, mapStep,
                              mapStride, ssim != nullptr, &job, false, 2);

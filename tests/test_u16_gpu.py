@@ -93,3 +93,20 @@ def test_u16_strided_layouts_and_device_api():
     for f in range(frames):
         of, _, omf = oracle_ssim_u16(np.roll(a, 5 * f, axis=1).copy(), np.roll(b, 5 * f, axis=1).copy(), want_map=True)
         assert abs(float(ds[f]) - float(of)) <= GLOBAL_TOL and np.abs(dm[f].cpu().numpy() - omf).max() <= PIXEL_TOL
+
+
+def test_u16_pipelined_host_path_equals_single_shot(monkeypatch):
+    """Large plain-row host images take the chunked H2D / kernel / D2H pipeline; results must match the single-shot path
+    (up to the per-item centring, which follows the chunk boundaries) and the oracle."""
+    from oracle import oracle_ssim_u16
+    from ssim_b200 import api
+    a, b = _pair16(1200, 1600, 3)
+    s1, m1 = api.compute_u16(a, b, want_map=True)                      # pipelined (>= 2^20 pixels)
+    monkeypatch.setenv("SSIM_CUDA_NO_PIPELINE", "1")
+    s2, m2 = api.compute_u16(a, b, want_map=True)                      # single shot
+    monkeypatch.delenv("SSIM_CUDA_NO_PIPELINE")
+    o, _, om = oracle_ssim_u16(a, b, want_map=True)
+    assert np.abs(m1 - m2).max() <= 3e-4 and abs(float(s1) - float(s2)) <= 2e-7
+    assert abs(float(s1) - float(o)) <= GLOBAL_TOL and np.abs(m1 - om).max() <= PIXEL_TOL
+    sn, _ = api.compute_u16(a, b, want_map=False)
+    assert abs(float(sn) - float(s1)) <= 2e-7
