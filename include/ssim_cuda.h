@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SSIM_CUDA_ABI_VERSION 1
+#define SSIM_CUDA_ABI_VERSION 2
 
 int         ssim_cuda_abi_version(void);
 int         ssim_cuda_device_count(void);            /* 0 when there is no driver / device */
@@ -82,7 +82,7 @@ int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint
 
 /*
  * Device-resident planes, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
- * stream).  `frames` independent pairs are processed by ONE kernel launch (+ one small reduction launch).
+ * stream).  `frames` independent pairs are processed by ONE kernel launch, reduction included.
  *
  *   dA/dB      8-bit planes, 1 byte per pixel; pixel (x,y) of frame f at d[f*frameStride + y*pitch + x].
  *              Base address, pitch and frameStride must be multiples of 16 bytes (TMA requirement).
@@ -122,13 +122,15 @@ int ssim_cuda_compute_device_u16(int device, void* stream,
                                  float* dMap, size_t mapPitch, size_t mapFrameStride,
                                  double* dSums, float* dSsim);
 
-/* Number of kernels the previous ssim_cuda_compute_device() call on this thread launched (for bench.py) */
+/* Number of kernels the previous ssim_cuda_compute_device() call on this thread launched (for bench.py): 1 */
 int ssim_cuda_last_launch_count(void);
 
 /*
  * One host image pair split into horizontal strips (with 5 halo rows on interior edges) across
- * `nDevices` GPUs of this process; the per-GPU double sums are combined with ncclAllReduce.
- * Same argument meaning as ssim_cuda_compute(); pointers must be host pointers.
+ * `nDevices` GPUs of this process.  The per-GPU double sums are combined INSIDE the kernels: the last warp of every
+ * GPU's launch stores its strip sum into the peers' exchange buffers over NVLink and adds up what lands in its own
+ * (see ssim_cuda_compute_strip_allreduce below); SSIM_CUDA_STRIPS_NCCL=1 selects one ncclAllReduce of a double per GPU
+ * instead.  Same argument meaning as ssim_cuda_compute(); pointers must be host pointers.
  */
 int ssim_cuda_compute_strips(int nDevices, const int* devices, uint32_t width, uint32_t height,
                              const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
@@ -168,8 +170,12 @@ int ssim_cuda_compute_strip_allreduce(int device, void* stream,
 int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, uint8_t* dB, size_t pitchB,
                          uint32_t width, uint32_t rows, uint32_t y0, uint32_t frame, uint64_t seed);
 
-/* Tuning knob (0 = automatic): rows per warp work item of the fused kernel.  For experiments/bench only. */
-void ssim_cuda_set_segment_rows(int rows);
+/*
+ * Tuning knobs of the persistent kernel's work partition, for experiments/bench only (0 = automatic for either):
+ * maxCtasPerSm caps the resident CTAs per SM the grid is sized for (1 or 2), minSlotRows is the smallest share of rows
+ * (incl. the 10 start-up rows per column) a warp pair is given before fewer pairs are used.  Process-wide.
+ */
+void ssim_cuda_set_tuning(int maxCtasPerSm, int minSlotRows);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,7 @@
   liboracle.so          our plain-C double restatement (oracle/ssim_oracle.c)
   _ref/libref_f32.so    the unmodified reference, float build  (CPU baseline "B")
   _ref/libref_f64.so    the unmodified reference, double build (gating oracle: "O1" AUTO, "O2" GENERIC)
+  _ref/libnaive.so      the reference's own test oracle tests/ssim_naive.h, <double, uint8_t> and <double, uint16_t>
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this."""
 import ctypes as C
@@ -34,6 +35,25 @@ def _load(path):
 
 def have_ref():
     return all(os.path.exists(os.path.join(HERE, "_ref", n)) for n in ("libref_f32.so", "libref_f64.so"))
+
+
+def have_naive():
+    return os.path.exists(os.path.join(HERE, "_ref", "libnaive.so"))
+
+
+def naive_ssim(a, b, want_map=False):
+    """The reference's naive::compute_ssim<double, T> (tests/ssim_naive.h:230-339) on contiguous uint8 or uint16 arrays:
+    T follows the dtype, so uint16 input means L = 65535.  Returns (double mean, float64 map or None)."""
+    assert a.dtype == b.dtype and a.dtype in (np.uint8, np.uint16) and a.flags.c_contiguous and b.flags.c_contiguous
+    lib = _load(os.path.join(HERE, "_ref", "libnaive.so"))
+    fn = lib.naive_ssim_u16 if a.dtype == np.uint16 else lib.naive_ssim_u8
+    fn.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_ssize_t, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_ssize_t,
+                   C.c_void_p, C.c_ssize_t, C.c_ssize_t]
+    fn.restype = C.c_double
+    h, w = a.shape
+    m = np.empty((h, w), dtype=np.float64) if want_map else None
+    s = fn(w, h, a.ctypes.data, 1, w, b.ctypes.data, 1, w, m.ctypes.data if want_map else None, 1, w)
+    return float(s), m
 
 
 def oracle_lib():

@@ -189,9 +189,12 @@ int ssim_oracle_compute(uint32_t width, uint32_t height,
     return oracle_core(width, height, 1, 255.0, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, tapsMode, ssim, sumOut);
 }
 
-/* 16-bit pixels, L = 65535: the extension the reference's README names (README.md:107-111) but does not implement.
- * PARITY UNPINNED against the reference (there is nothing to run); pinned instead by the scale invariance
- * SSIM_16(257 a, 257 b) == SSIM_8(a, b), which tests/test_oracle.py checks against the pinned 8-bit path. */
+/* 16-bit pixels, L = 65535: the extension the reference's README names (README.md:107-111); the library does not
+ * implement it, but the reference's own test oracle does: tests/ssim_naive.h:230-241 is a template on the pixel type T with
+ * L = numeric_limits<T>::max().  PARITY PINNED to naive::compute_ssim<double, uint16_t> (compiled in place into
+ * oracle/_ref/libnaive.so): tests/test_oracle.py checks this function against the vectors that shim produced
+ * (tests/golden/golden.json "u16_naive", tests/golden/u16_pair.npz) and live against the shim, to 1e-12 on the double
+ * mean with TAPS_RUNTIME; the scale invariance SSIM_16(257 a, 257 b) == SSIM_8(a, b) is checked as well. */
 int ssim_oracle_compute_u16(uint32_t width, uint32_t height,
                             const uint16_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
                             const uint16_t* b, ptrdiff_t stepB, ptrdiff_t strideB,

@@ -78,8 +78,8 @@ def cuda_lib():
     lib.ssim_cuda_synth_fill.argtypes = [C.c_int, vp, u8p, C.c_size_t, u8p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.c_uint32, C.c_uint64]
     lib.ssim_cuda_synth_fill.restype = C.c_int
-    lib.ssim_cuda_set_segment_rows.argtypes = [C.c_int]
-    lib.ssim_cuda_set_segment_rows.restype = None
+    lib.ssim_cuda_set_tuning.argtypes = [C.c_int, C.c_int]
+    lib.ssim_cuda_set_tuning.restype = None
     lib._bound = True
     return lib
 

@@ -17,6 +17,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cmath>
 #include <cstdarg>
@@ -24,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -35,7 +37,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------ errors
 thread_local char g_err[512] = "";
 thread_local int  g_lastLaunches = 0;
-int g_segRowsOverride = 0;
+std::atomic<int> g_minSlotRows{0};       // tuning knobs (0 = automatic), see ssim_cuda_set_tuning()
+std::atomic<int> g_maxCtasPerSm{0};
 
 int fail(int code, const char* fmt, ...)
 {
@@ -60,6 +63,25 @@ int cuda_fail(cudaError_t e, const char* what)
         cudaError_t e__ = (expr);                                      \
         if (e__ != cudaSuccess) return cuda_fail(e__, #expr);          \
     } while (0)
+
+// Every entry point that needs `device` current makes it so through this guard and puts the caller's device back on
+// return: a host application (or a PyTorch thread) whose own CUDA work runs on another device is not switched silently.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != device) { err = cudaSetDevice(device); switched = (err == cudaSuccess); }
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_GUARD(dev)                                              \
+    DeviceGuard guard__(dev);                                          \
+    if (guard__.err != cudaSuccess) return cuda_fail(guard__.err, "cudaSetDevice")
 
 // ------------------------------------------------------------------------------------------------ Gaussian taps
 // The window every shipped build of the reference actually applies is its FLOAT 11x11 kernel: the generic blur
@@ -126,18 +148,54 @@ EncodeTiledFn encode_fn()
 }
 
 int make_plane_map(CUtensorMap* tm, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
-                   size_t frameStride, uint32_t boxRows, int elemBytes = 1)
+                   size_t frameStride, int elemBytes)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(EIO, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3]    = {width, rows, frames};
     const cuuint64_t strides[2] = {pitch, frames > 1 ? frameStride : (cuuint64_t)pitch * rows};
-    const cuuint32_t box[3]     = {(cuuint32_t)(elemBytes == 2 ? ssimk::PixGeo<true>::kBoxElems : ssimk::PixGeo<false>::kBoxElems), boxRows, 1};
+    const cuuint32_t box[3]     = {(cuuint32_t)(elemBytes == 2 ? ssimk::PixGeo<true>::kBoxElems : ssimk::PixGeo<false>::kBoxElems), (cuuint32_t)ssimk::kLoadRows, 1};
     const cuuint32_t estr[3]    = {1, 1, 1};
     CUresult r = enc(tm, elemBytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EIO, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u pitch %zu", (int)r, width, rows, frames, pitch);
+    return 0;
+}
+
+// Descriptor cache: a video sweep or a pipelined host call presents the same (pointer, geometry) again and again (frame
+// rings, the context's own scratch planes), and encoding a tensor map costs a driver call of a few microseconds -- as much
+// as the kernel launch itself.  Per thread (no lock), 16 entries, round-robin replacement.  A descriptor only holds the
+// address and the geometry, so a hit on a pointer that was freed and re-allocated with the same geometry is still right.
+struct MapKey {
+    const uint8_t* base; size_t pitch, frameStride; uint32_t width, rows, frames; int elemBytes;
+    bool operator==(const MapKey& o) const
+    {
+        return base == o.base && pitch == o.pitch && frameStride == o.frameStride && width == o.width && rows == o.rows &&
+               frames == o.frames && elemBytes == o.elemBytes;
+    }
+};
+struct MapCache {
+    static const int kEntries = 16;
+    MapKey key[kEntries];
+    alignas(64) CUtensorMap tm[kEntries];
+    int used = 0, next = 0;
+};
+thread_local MapCache g_mapCache;
+
+int get_plane_map(const CUtensorMap** out, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
+                  size_t frameStride, int elemBytes)
+{
+    MapCache& mc = g_mapCache;
+    const MapKey k = {base, pitch, frames > 1 ? frameStride : 0, width, rows, frames, elemBytes};
+    for (int i = 0; i < mc.used; ++i)
+        if (mc.key[i] == k) { *out = &mc.tm[i]; return 0; }
+    const int slot = mc.used < MapCache::kEntries ? mc.used : mc.next;
+    int rc = make_plane_map(&mc.tm[slot], base, width, rows, frames, pitch, frameStride, elemBytes);
+    if (rc) { if (slot < mc.used) mc.key[slot].base = nullptr; return rc; }
+    mc.key[slot] = k;
+    if (mc.used < MapCache::kEntries) ++mc.used; else mc.next = (mc.next + 1) % MapCache::kEntries;
+    *out = &mc.tm[slot];
     return 0;
 }
 
@@ -163,10 +221,17 @@ struct Buffer {
     }
 };
 
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {             // reduction workspace of one stream, see get_workspace()
+    Buffer buf;
+    size_t counters = 0;       // capacity of the counter region, in frames
+};
+
 struct Context {
     int device = -1;
     int numSMs = 0;
-    int ctasPerSm = 3;
+    int ctasPerSm = ssimk::kCtasPerSm;
     cudaStream_t stream = nullptr;            // stream of the blocking host-pointer path (compute)
     cudaStream_t streamIn = nullptr;          // pipelined host path: H2D copies
     cudaStream_t streamOut = nullptr;         // pipelined host path: D2H copies
@@ -177,12 +242,32 @@ struct Context {
     Buffer planeA, planeB, rawA, rawB, map, stage;
     Buffer scalars;                           // double sum + float ssim of the host path
     std::mutex wsMutex;
-    std::map<cudaStream_t, Buffer> partials;  // per-stream partial-sum workspace of compute_device
+    std::map<cudaStream_t, Workspace> workspaces;   // per-stream reduction workspace of the fused kernel
+    std::vector<void*> retired;               // outgrown workspaces: work queued earlier may still use them, freed at shutdown
     float taps[6];
+    float eps2 = 0.f;
+
+    ~Context()
+    {
+        // RAII: also runs when create_context() fails half-way (nothing leaks on its error paths)
+        if (device < 0) return;
+        DeviceGuard g(device);
+        cudaDeviceSynchronize();
+        for (Buffer* b : {&planeA, &planeB, &rawA, &rawB, &map, &stage, &scalars, &chunkSums, &chunkSumsHost}) b->release();
+        for (int i = 0; i < kMaxChunks; ++i) { if (evIn[i]) cudaEventDestroy(evIn[i]); if (evDone[i]) cudaEventDestroy(evDone[i]); }
+        if (streamIn) cudaStreamDestroy(streamIn);
+        if (streamOut) cudaStreamDestroy(streamOut);
+        for (auto& p : workspaces) p.second.buf.release();
+        for (void* p : retired) cudaFree(p);
+        if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();
+    }
 };
 
 std::mutex g_ctxMutex;
 std::map<int, Context*> g_ctx;
+const int kFastDevices = 64;
+std::atomic<Context*> g_ctxFast[kFastDevices];     // lock-free lookup for the hot device-pointer path
 
 int create_context(int device, Context** out)
 {
@@ -190,15 +275,20 @@ int create_context(int device, Context** out)
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) { cudaGetLastError(); return fail(ENODEV, "no usable CUDA device (%s)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)); }
     if (device < 0 || device >= count) return fail(EINVAL, "device %d out of range [0,%d)", device, count);
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
-    Context* c = new Context();
+    std::unique_ptr<Context> c(new Context());
     c->device = device;
     c->numSMs = prop.multiProcessorCount;
     c->stage.pinnedHost = true;
     gaussian_taps(c->taps);
+    {
+        double s1 = (double)c->taps[0];
+        for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];
+        c->eps2 = (float)(2.0 * (s1 * s1 - 1.0));
+    }
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->streamIn, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->streamOut, cudaStreamNonBlocking));
@@ -209,26 +299,20 @@ int create_context(int device, Context** out)
     c->chunkSumsHost.pinnedHost = true;
     int regsMap = 0, regsNoMap = 0, ctas = 0;
     CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &ctas));
-    c->ctasPerSm = std::max(1, ctas);
-    *out = c;
+    // the kernel is persistent: its grid must be resident at once, so never plan for more CTAs per SM than actually fit
+    c->ctasPerSm = std::max(1, std::min(ctas, ssimk::kCtasPerSm));
+    *out = c.release();
     return 0;
 }
 
-void destroy_context(Context* c)
-{
-    cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
-    for (Buffer* b : {&c->planeA, &c->planeB, &c->rawA, &c->rawB, &c->map, &c->stage, &c->scalars, &c->chunkSums, &c->chunkSumsHost}) b->release();
-    for (int i = 0; i < Context::kMaxChunks; ++i) { if (c->evIn[i]) cudaEventDestroy(c->evIn[i]); if (c->evDone[i]) cudaEventDestroy(c->evDone[i]); }
-    if (c->streamIn) cudaStreamDestroy(c->streamIn);
-    if (c->streamOut) cudaStreamDestroy(c->streamOut);
-    for (auto& p : c->partials) p.second.release();
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
-}
+void destroy_context(Context* c) { delete c; }
 
 int get_context(int device, Context** out)
 {
+    if (device >= 0 && device < kFastDevices) {
+        Context* c = g_ctxFast[device].load(std::memory_order_acquire);
+        if (c) { *out = c; return 0; }
+    }
     std::lock_guard<std::mutex> lock(g_ctxMutex);
     auto it = g_ctx.find(device);
     if (it != g_ctx.end()) { *out = it->second; return 0; }
@@ -236,6 +320,7 @@ int get_context(int device, Context** out)
     int rc = create_context(device, &c);
     if (rc) return rc;
     g_ctx[device] = c;
+    if (device < kFastDevices) g_ctxFast[device].store(c, std::memory_order_release);
     *out = c;
     return 0;
 }
@@ -274,53 +359,64 @@ int acquire_host_context(Context** c, std::unique_lock<std::mutex>* lock)
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ work decomposition
-// A work item is (frame, row segment, 64-column band) and is executed by one warp.  Each item pays a fixed
-// 10-row halo (horizontal pass recomputed, vertical pipeline fill), so segments should be tall; but a single
-// 4K image only has 60 bands, so segments must also be numerous enough to occupy ctasPerSm*4 warps on every SM.
-void choose_segments(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, int* segRows, int* segs)
+// ------------------------------------------------------------------------------------------------ work partition + launch
+// See "work partition" in ssim_kernels.h: the persistent grid's warp pairs ("slots") share the rows of all (frame, band)
+// columns evenly.  The only choices left to the host are how many CTAs per SM to use and how thin the work may be spread
+// (a slot pays 10 start-up rows, so tiny inputs use fewer slots).
+const uint32_t kDefaultMinSlotRows = 24;
+
+bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, ssimk::SlotPlan* plan)
 {
-    ssimk::plan_segments((long long)c->numSMs * c->ctasPerSm, width, outRows, frames, g_segRowsOverride, segRows, segs);
+    int ctas = g_maxCtasPerSm.load(std::memory_order_relaxed);
+    if (ctas <= 0 || ctas > c->ctasPerSm) ctas = c->ctasPerSm;
+    const int minRows = g_minSlotRows.load(std::memory_order_relaxed);
+    return ssimk::plan_slots((uint32_t)(c->numSMs * ctas * ssimk::kPairsPerCta), width, outRows, frames,
+                             minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan);
 }
 
-int get_partials(Context* c, cudaStream_t stream, size_t bytes, double** out)
+// Reduction workspace of a stream: per-frame arrival counters (zero between launches: the kernel resets them), then
+// slots*entries doubles.  Launches on one stream run in order, so they can share it.  A workspace that has become too
+// small is retired, not freed: work queued earlier on the stream may still be using it.
+struct WorkspaceView { unsigned* frameDone; double* partials; };
+
+int get_workspace(Context* c, cudaStream_t stream, size_t frames, size_t cells, WorkspaceView* out)
 {
     std::lock_guard<std::mutex> lock(c->wsMutex);
-    Buffer& b = c->partials[stream];
-    if (bytes > b.cap) {
-        // the old buffer may still be in use by work queued on this stream
-        if (b.ptr) CU_TRY(cudaStreamSynchronize(stream));
-        int rc = b.ensure(std::max<size_t>(bytes, 1 << 20));
-        if (rc) return rc;
+    auto it = c->workspaces.find(stream);
+    if (it == c->workspaces.end()) {
+        if (c->workspaces.size() >= 64) {
+            // stream handles come and go in a long-lived process: start over instead of growing without bound
+            CU_TRY(cudaDeviceSynchronize());
+            for (auto& p : c->workspaces) p.second.buf.release();
+            for (void* p : c->retired) cudaFree(p);
+            c->workspaces.clear();
+            c->retired.clear();
+        }
+        it = c->workspaces.emplace(stream, Workspace()).first;
     }
-    *out = (double*)b.ptr;
+    Workspace& w = it->second;
+    if (frames > w.counters || w.counters * sizeof(unsigned) + cells * sizeof(double) > w.buf.cap) {
+        if (w.buf.ptr) { c->retired.push_back(w.buf.ptr); w.buf.ptr = nullptr; w.buf.cap = 0; }
+        w.counters = align_up(std::max<size_t>(2 * frames, 1024), 4);
+        const size_t bytes = w.counters * sizeof(unsigned) + std::max<size_t>(2 * cells, 4096) * sizeof(double);
+        int rc = w.buf.ensure(bytes);
+        if (rc) { w.counters = 0; return rc; }
+        CU_TRY(cudaMemsetAsync(w.buf.ptr, 0, w.counters * sizeof(unsigned), stream));
+    }
+    out->frameDone = (unsigned*)w.buf.ptr;
+    out->partials = (double*)((char*)w.buf.ptr + w.counters * sizeof(unsigned));
     return 0;
-}
-
-// Chunked callers (the pipelined host path) encode the two tensor maps once, hand every chunk a slice of one partial-sum
-// buffer and run a single finalize at the end: per chunk that leaves exactly one kernel launch.
-struct ChunkPlan {
-    const CUtensorMap* maps = nullptr;      // {A, B}, encoded once for the whole plane
-    double* partials = nullptr;             // this chunk's slice
-    long long* itemsOut = nullptr;          // receives the number of partials written
-};
-
-long long plan_items(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames)
-{
-    int segRows, segs;
-    choose_segments(c, width, outRows, frames, &segRows, &segs);
-    return (long long)((width + ssimk::kBandW - 1) / ssimk::kBandW) * segs * frames;
 }
 
 int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
                         uint32_t frames, const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB,
                         size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim,
-                        const ChunkPlan* chunk = nullptr, int elemBytes = 1, const ssimk::ExchangeParams* xchg = nullptr)
+                        int elemBytes = 1, const ssimk::ExchangeParams* xchg = nullptr)
 {
     g_lastLaunches = 0;
     if (width == 0 || srcRows == 0 || outRows == 0 || frames == 0) return fail(EINVAL, "width, rows and frames must be non-zero");
     if (dA == nullptr || dB == nullptr) return fail(EINVAL, "dA or dB is NULL");
-    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr && chunk == nullptr && xchg == nullptr) return fail(EINVAL, "no output requested");
+    if (dMap == nullptr && dSums == nullptr && dSsim == nullptr && xchg == nullptr) return fail(EINVAL, "no output requested");
     if ((uint64_t)outY0 + outRows > srcRows) return fail(EINVAL, "output rows [%u,%u) exceed the %u source rows", outY0, outY0 + outRows, srcRows);
     if (width > 0x7fffff00u || srcRows > 0x7fffff00u) return fail(EINVAL, "dimensions too large");
     if (((uintptr_t)dA | (uintptr_t)dB | pitchA | pitchB) & 15) return fail(EINVAL, "plane base addresses and pitches must be multiples of 16 bytes");
@@ -328,26 +424,15 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (pitchA < (size_t)width * elemBytes || pitchB < (size_t)width * elemBytes) return fail(EINVAL, "pitch smaller than width");
     if (dMap && mapPitch < width) return fail(EINVAL, "map pitch smaller than width");
 
-    int segRows, segs;
-    choose_segments(c, width, outRows, frames, &segRows, &segs);
-    const int bands = (int)((width + ssimk::kBandW - 1) / ssimk::kBandW);
-    const long long itemsPerFrame = (long long)bands * segs;
-    const long long items = itemsPerFrame * frames;
-    if (itemsPerFrame > 0x7fffffffLL || items > 0x7fffffffLL) return fail(EINVAL, "image or batch too large");
+    ssimk::SlotPlan plan;
+    if (!plan_for(c, width, outRows, frames, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
 
-    double* partials = nullptr;
-    int rc = 0;
-    CUtensorMap local[2];
-    const CUtensorMap* tm = local;
-    if (chunk) {
-        partials = chunk->partials;
-        tm = chunk->maps;
-        if (chunk->itemsOut) *chunk->itemsOut = items;
-    } else {
-        if ((rc = get_partials(c, stream, (size_t)items * sizeof(double), &partials))) return rc;
-        if ((rc = make_plane_map(&local[0], dA, width, srcRows, frames, pitchA, frameStrideA, ssimk::kLoadRows, elemBytes))) return rc;
-        if ((rc = make_plane_map(&local[1], dB, width, srcRows, frames, pitchB, frameStrideB, ssimk::kLoadRows, elemBytes))) return rc;
-    }
+    WorkspaceView ws;
+    int rc = get_workspace(c, stream, frames, (size_t)plan.slots * plan.entries, &ws);
+    if (rc) return rc;
+    const CUtensorMap *tmA, *tmB;
+    if ((rc = get_plane_map(&tmA, dA, width, srcRows, frames, pitchA, frameStrideA, elemBytes))) return rc;
+    if ((rc = get_plane_map(&tmB, dB, width, srcRows, frames, pitchB, frameStrideB, elemBytes))) return rc;
 
     ssimk::FusedParams p;
     memset(&p, 0, sizeof(p));
@@ -356,36 +441,20 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
     p.pitchB = (long long)pitchB; p.frameStrideB = (long long)frameStrideB;
     p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride;
-    p.partials = partials;
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
-    p.bands = bands; p.segs = segs; p.segRows = segRows; p.items = items;
-    ssimk::fast_div((uint32_t)bands, &p.bandsMul, &p.bandsShift);
-    ssimk::fast_div((uint32_t)segs, &p.segsMul, &p.segsShift);
+    p.geo = ssimk::make_slot_geo(plan, width);
+    p.partials = ws.partials; p.frameDone = ws.frameDone; p.entries = plan.entries;
+    p.sums = dSums; p.ssim = dSsim;
+    p.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];
-    p.c1 = (float)((0.01 * 255) * (0.01 * 255));      // src/ssim.cpp:956-960
-    p.c2 = (float)((0.03 * 255) * (0.03 * 255));
     p.magic = 0x4B000000u;
     {
         static const unsigned backoff = [] { const char* e = getenv("SSIM_CUDA_BACKOFF_NS"); return e ? (unsigned)atoi(e) : ssimk::kBackoffNs; }();
         p.backoffNs = backoff;
     }
-    {
-        double s1 = (double)c->taps[0];
-        for (int d = 1; d < 6; ++d) s1 += 2.0 * (double)c->taps[d];
-        p.eps2 = (float)(2.0 * (s1 * s1 - 1.0));
-    }
-    CU_TRY(ssimk::launch_fused(stream, tm[0], tm[1], p));
+    p.eps2 = c->eps2;
+    CU_TRY(ssimk::launch_fused(stream, *tmA, *tmB, p, xchg));      // the ONLY launch: reduction (and exchange) happen inside
     g_lastLaunches = 1;
-
-    if (!chunk && (dSums || dSsim || xchg)) {
-        ssimk::FinalizeParams f;
-        f.partials = partials; f.sums = dSums; f.ssim = dSsim;
-        f.itemsPerFrame = (int)itemsPerFrame;
-        f.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
-        if (xchg) CU_TRY(ssimk::launch_finalize_allreduce(stream, f, *xchg));     // one strip: reduction + cross-GPU sum in one kernel
-        else      CU_TRY(ssimk::launch_finalize(stream, f, (int)frames));
-        g_lastLaunches = 2;
-    }
     return 0;
 }
 
@@ -398,8 +467,6 @@ Where classify(const void* p)
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return Where::Host; }
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? Where::Device : Where::Host;
 }
-
-size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Brings one strided image into a canonical plane (dense rows, 16-byte aligned pitch) in device memory.
 // On return *plane/*pitch describe it; it is either the caller's own memory (already canonical) or ctx scratch.
@@ -471,9 +538,10 @@ struct GeneralJob {
 
 int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, uint32_t outRows, const uint8_t* a, ptrdiff_t stepA,
                     ptrdiff_t strideA, const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep,
-                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job, bool luma = false, int elemBytes = 1)
+                    ptrdiff_t mapStride, bool wantSsim, GeneralJob* job, bool luma = false, int elemBytes = 1,
+                    const ssimk::ExchangeParams* xchg = nullptr)
 {
-    CU_TRY(cudaSetDevice(c->device));
+    DEVICE_GUARD(c->device);
     cudaStream_t s = c->stream;
     const uint8_t *pa, *pb;
     size_t pitchA, pitchB;
@@ -501,7 +569,7 @@ int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, ui
     float* dSsim = (float*)((char*)c->scalars.ptr + 8);
 
     rc = compute_device_impl(c, s, W, srcRows, outY0, outRows, 1, pa, pitchA, 0, pb, pitchB, 0, dMap, dMapPitch, 0, dSum,
-                             wantSsim ? dSsim : nullptr, nullptr, elemBytes);
+                             wantSsim ? dSsim : nullptr, elemBytes, xchg);
     if (rc) return rc;
 
     job->c = c; job->W = W; job->outRows = outRows; job->map = map; job->mapStep = mapStep; job->mapStride = mapStride;
@@ -526,7 +594,7 @@ int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, ui
 
 int finish_general(const GeneralJob& job)
 {
-    CU_TRY(cudaSetDevice(job.c->device));
+    DEVICE_GUARD(job.c->device);
     CU_TRY(cudaStreamSynchronize(job.c->stream));
     if (job.cpuScatter) {
         const float* src = (const float*)job.c->stage.ptr;
@@ -537,16 +605,18 @@ int finish_general(const GeneralJob& job)
     return 0;
 }
 
+const uint64_t kPipelineMinBytes = 1u << 21;      // images of at least 2 MB take the chunked copy/compute pipeline
+
 // Large host images in plain row layout: the image is cut into row chunks and three streams overlap the H2D copy of
 // chunk k+1, the kernel of chunk k and the map D2H of chunk k-1 (PCIe is full duplex; the kernel is ~10x faster than
 // either copy, so a blocking call costs about max(H2D, D2H) instead of H2D + kernel + D2H).  A chunk's kernel reads rows
 // up to 5 below its last output row, so its H2D covers 5 extra rows; everything lands in one full-height device plane and
 // the kernel addresses it with (srcRows = H, outY0, outRows), i.e. exactly the strip mechanism of the multi-GPU path.
-int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t strideA, const uint8_t* b, ptrdiff_t strideB,
-                      float* map, ptrdiff_t mapStride, float* ssim, int elemBytes = 1)
+int compute_pipelined_body(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t strideA, const uint8_t* b, ptrdiff_t strideB,
+                           float* map, ptrdiff_t mapStride, float* ssim, int elemBytes)
 {
     // a, b: byte pointers; strideA/strideB in BYTES; elemBytes = 1 (8-bit) or 2 (16-bit pixels)
-    CU_TRY(cudaSetDevice(c->device));
+    DEVICE_GUARD(c->device);
     const size_t rowBytes = (size_t)W * elemBytes;
     const size_t pitch = align_up(rowBytes, 16), mapPitch = align_up(W, 4);
     int rc;
@@ -565,20 +635,9 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
     float* dMap = map ? (float*)c->map.ptr : nullptr;
     double* dSums = (double*)c->chunkSums.ptr;
 
-    // tensor maps of the whole planes, encoded once; one partial-sum buffer for all chunks, one finalize at the end
-    CUtensorMap maps[2];
-    if ((rc = make_plane_map(&maps[0], dA, W, H, 1, pitch, 0, ssimk::kLoadRows, elemBytes)) ||
-        (rc = make_plane_map(&maps[1], dB, W, H, 1, pitch, 0, ssimk::kLoadRows, elemBytes))) return rc;
-    long long totalItems = 0;
-    for (int k = 0; k < nChunks; ++k) {
-        const uint32_t y0 = bounds[k], y1 = bounds[k + 1];
-        if (y1 > y0) totalItems += plan_items(c, W, y1 - y0, 1);
-    }
-    double* partials = nullptr;
-    if ((rc = get_partials(c, c->stream, (size_t)totalItems * sizeof(double), &partials))) return rc;
-
+    // Every chunk is ONE launch: the tensor maps of the whole planes come from the descriptor cache (encoded by the first
+    // chunk, the context's scratch planes rarely move), and each launch leaves its chunk's double sum in dSums[k].
     uint32_t copied = 0;                                       // rows [0, copied) are on the device (or in flight on streamIn)
-    long long itemsDone = 0;
     for (int k = 0; k < nChunks; ++k) {
         const uint32_t y0 = bounds[k], y1 = bounds[k + 1];
         const uint32_t need = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
@@ -592,13 +651,9 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
         if (y1 == y0) continue;
         CU_TRY(cudaEventRecord(c->evIn[k], c->streamIn));
         CU_TRY(cudaStreamWaitEvent(c->stream, c->evIn[k], 0));
-        ChunkPlan plan;
-        long long items = 0;
-        plan.maps = maps; plan.partials = partials + itemsDone; plan.itemsOut = &items;
         rc = compute_device_impl(c, c->stream, W, H, y0, y1 - y0, 1, dA, pitch, 0, dB, pitch, 0,
-                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, nullptr, nullptr, &plan, elemBytes);
+                                 dMap ? dMap + (size_t)y0 * mapPitch : nullptr, mapPitch, 0, dSums + k, nullptr, elemBytes);
         if (rc) return rc;
-        itemsDone += items;
         if (map) {
             CU_TRY(cudaEventRecord(c->evDone[k], c->stream));
             CU_TRY(cudaStreamWaitEvent(c->streamOut, c->evDone[k], 0));
@@ -606,14 +661,54 @@ int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrd
                                      mapPitch * sizeof(float), (size_t)W * sizeof(float), y1 - y0, cudaMemcpyDeviceToHost, c->streamOut));
         }
     }
-    // all chunks' partials in one fixed-order reduction (deterministic), then the reference's last step (src/ssim.cpp:1102)
-    ssimk::FinalizeParams f;
-    f.partials = partials; f.sums = dSums; f.ssim = nullptr; f.itemsPerFrame = (int)itemsDone; f.invCount = 0.0;
-    CU_TRY(ssimk::launch_finalize(c->stream, f, 1));
-    CU_TRY(cudaMemcpyAsync(c->chunkSumsHost.ptr, dSums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // the chunk sums in chunk order (deterministic), then the reference's last step (src/ssim.cpp:1102)
+    CU_TRY(cudaMemcpyAsync(c->chunkSumsHost.ptr, dSums, sizeof(double) * nChunks, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (map) CU_TRY(cudaStreamSynchronize(c->streamOut));
-    if (ssim) *ssim = (float)(((const double*)c->chunkSumsHost.ptr)[0] / (double)(uint32_t)(W * H));
+    if (ssim) {
+        double total = 0.0;
+        for (int k = 0; k < nChunks; ++k)
+            if (bounds[k + 1] > bounds[k]) total += ((const double*)c->chunkSumsHost.ptr)[k];
+        *ssim = (float)(total / (double)(uint32_t)(W * H));
+    }
+    return 0;
+}
+
+// A failed call must not leave copies in flight on the caller's memory (include/ssim_cuda.h: "a call never retains caller
+// pointers"): error paths of the host-pointer entry points drain the context's streams before returning.
+int drained(Context* c, int rc)
+{
+    if (rc) {
+        DeviceGuard g(c->device);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->streamIn);
+        cudaStreamSynchronize(c->streamOut);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+int compute_pipelined(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t strideA, const uint8_t* b, ptrdiff_t strideB,
+                      float* map, ptrdiff_t mapStride, float* ssim, int elemBytes = 1)
+{
+    return drained(c, compute_pipelined_body(c, W, H, a, strideA, b, strideB, map, mapStride, ssim, elemBytes));
+}
+
+// Brings the float result of an enqueued general job back (through the context's pinned scalars) and completes the job.
+int finish_with_scalar(Context* c, const GeneralJob& job, float* ssim)
+{
+    int rc = 0;
+    {
+        DeviceGuard g(c->device);
+        if (ssim) {
+            rc = c->chunkSumsHost.ensure(sizeof(double) * Context::kMaxChunks);
+            if (!rc && cudaMemcpyAsync(c->chunkSumsHost.ptr, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(ssim)");
+        }
+    }
+    if (!rc) rc = finish_general(job);
+    if (rc) return drained(c, rc);
+    if (ssim) *ssim = *(const float*)c->chunkSumsHost.ptr;
     return 0;
 }
 
@@ -624,19 +719,15 @@ int compute_general(Context* c, uint32_t W, uint32_t H, const uint8_t* a, ptrdif
     if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
     // pipelined path: plain-row host images (and host map) large enough for the overlap to pay.  Pageable memory works
     // too (the runtime stages it), pinned memory gets the full overlap.
-    if ((uint64_t)W * H >= (1u << 21) && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
+    if ((uint64_t)W * H >= kPipelineMinBytes && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
         classify(a) == Where::Host && classify(b) == Where::Host &&
         (map == nullptr || (mapStep == 1 && mapStride >= (ptrdiff_t)W && classify(map) == Where::Host)) &&
         getenv("SSIM_CUDA_NO_PIPELINE") == nullptr)
         return compute_pipelined(c, W, H, a, strideA, b, strideB, map, mapStride, ssim);
     GeneralJob job;
     int rc = enqueue_general(c, W, H, 0, H, a, stepA, strideA, b, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job);
-    if (rc) return rc;
-    float hostSsim = 0.f;
-    if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = finish_general(job))) return rc;
-    if (ssim) *ssim = hostSsim;
-    return 0;
+    if (rc) return drained(c, rc);
+    return finish_with_scalar(c, job, ssim);
 }
 
 // 16-bit pixels: same machinery, element size 2, blocking single-shot path
@@ -645,8 +736,9 @@ int compute_general_u16(Context* c, uint32_t W, uint32_t H, const uint16_t* a, p
 {
     std::unique_lock<std::mutex> lock;
     if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
-    // same pipelined path as 8-bit images for large plain-row host images (H2D / kernel / D2H overlapped in row chunks)
-    if ((uint64_t)W * H >= (1u << 20) && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
+    // same pipelined path as 8-bit images for large plain-row host images (H2D / kernel / D2H overlapped in row chunks);
+    // the threshold is in BYTES of one image (2 MB, as for 8-bit pixels), hence half as many pixels
+    if ((uint64_t)W * H * 2 >= kPipelineMinBytes && stepA == 1 && stepB == 1 && strideA >= (ptrdiff_t)W && strideB >= (ptrdiff_t)W &&
         classify(a) == Where::Host && classify(b) == Where::Host &&
         (map == nullptr || (mapStep == 1 && mapStride >= (ptrdiff_t)W && classify(map) == Where::Host)) &&
         getenv("SSIM_CUDA_NO_PIPELINE") == nullptr)
@@ -654,12 +746,8 @@ int compute_general_u16(Context* c, uint32_t W, uint32_t H, const uint16_t* a, p
     GeneralJob job;
     int rc = enqueue_general(c, W, H, 0, H, (const uint8_t*)a, 2 * stepA, 2 * strideA, (const uint8_t*)b, 2 * stepB, 2 * strideB, map, mapStep,
                              mapStride, ssim != nullptr, &job, false, 2);
-    if (rc) return rc;
-    float hostSsim = 0.f;
-    if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = finish_general(job))) return rc;
-    if (ssim) *ssim = hostSsim;
-    return 0;
+    if (rc) return drained(c, rc);
+    return finish_with_scalar(c, job, ssim);
 }
 
 // ------------------------------------------------------------------------------------------------ NCCL (dlopen'ed)
@@ -707,9 +795,39 @@ int nccl_load()
         if (r__ != ncclSuccess) return fail(EIO, "%s: %s", #expr, g_nccl.GetErrorString(r__));  \
     } while (0)
 
+// ---- exchange buffers of a single process driving several GPUs (ssim_cuda_compute_strips)
+std::mutex g_xchgMutex;
+std::map<int, void*> g_xchgBuf;                       // device -> its exchange buffer
+std::map<std::pair<int, int>, bool> g_peerEnabled;    // (device, peer) pairs with peer access switched on
+std::atomic<unsigned long long> g_stripEpoch{0};
+
+int exchange_alloc(int device, void** out)
+{
+    DEVICE_GUARD(device);
+    const size_t bytes = 2 * ssimk::kMaxRanks * sizeof(ssimk::ExchangeSlot);
+    CU_TRY(cudaMalloc(out, bytes));
+    CU_TRY(cudaMemset(*out, 0, bytes));
+    CU_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+int enable_peer(int device, int peerDevice)
+{
+    if (device == peerDevice) return 0;
+    DEVICE_GUARD(device);
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peerDevice));
+    if (!can) return fail(ENODEV, "device %d cannot access device %d", device, peerDevice);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    CU_TRY(e);
+    return 0;
+}
+
 int compute_strips(int n, const int* devices, uint32_t W, uint32_t H, const uint8_t* a, ptrdiff_t stepA, ptrdiff_t strideA,
                    const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep, ptrdiff_t mapStride, float* ssim)
 {
+    if ((uint32_t)n > H) n = (int)H;                  // no empty strips: an image of fewer rows than devices uses fewer devices
     std::vector<Context*> ctx(n);
     for (int g = 0; g < n; ++g) {
         for (int k = 0; k < g; ++k)
@@ -717,8 +835,13 @@ int compute_strips(int n, const int* devices, uint32_t W, uint32_t H, const uint
         int rc = get_context(devices[g], &ctx[g]);
         if (rc) return rc;
     }
+    // The strip sums are combined inside the kernels over NVLink peer memory (ssimk::ExchangeParams); NCCL stays available
+    // as SSIM_CUDA_STRIPS_NCCL=1 (one ncclAllReduce of a double per GPU, as BASELINE.json's north star words it).
+    static const bool useNccl = [] { const char* e = getenv("SSIM_CUDA_STRIPS_NCCL"); return e && atoi(e) != 0; }();
+    if (n > ssimk::kMaxRanks && !useNccl) return fail(EINVAL, "at most %d devices", ssimk::kMaxRanks);
     std::vector<ncclComm_t>* comms = nullptr;
-    if (n > 1) {
+    std::vector<void*> xbuf(n, nullptr);
+    if (n > 1 && useNccl) {
         std::lock_guard<std::mutex> lock(g_nccl.mutex);
         int rc = nccl_load();
         if (rc) return rc;
@@ -730,6 +853,24 @@ int compute_strips(int n, const int* devices, uint32_t W, uint32_t H, const uint
             it = g_nccl.comms.emplace(key, c).first;
         }
         comms = &it->second;
+    } else if (n > 1) {
+        std::lock_guard<std::mutex> lock(g_xchgMutex);
+        for (int g = 0; g < n; ++g) {
+            auto it = g_xchgBuf.find(devices[g]);
+            if (it == g_xchgBuf.end()) {
+                void* buf = nullptr;
+                int rc = exchange_alloc(devices[g], &buf);
+                if (rc) return rc;
+                it = g_xchgBuf.emplace(devices[g], buf).first;
+            }
+            xbuf[g] = it->second;
+            for (int k = 0; k < n; ++k) {
+                if (k == g || g_peerEnabled.count({devices[g], devices[k]})) continue;
+                int rc = enable_peer(devices[g], devices[k]);
+                if (rc) return rc;
+                g_peerEnabled[{devices[g], devices[k]}] = true;
+            }
+        }
     }
     // lock the contexts in device order (no lock-order inversion between concurrent callers)
     std::vector<int> order(n);
@@ -738,38 +879,64 @@ int compute_strips(int n, const int* devices, uint32_t W, uint32_t H, const uint
     std::vector<std::unique_lock<std::mutex>> locks;
     for (int g : order) locks.emplace_back(ctx[g]->hostPathMutex);
 
+    auto fail_all = [&](int rc) { for (int g = 0; g < n; ++g) drained(ctx[g], rc); return rc; };
+
     // strip g produces rows [g*H/n, (g+1)*H/n) and reads 5 more rows on each interior edge (src/ssim.cpp:749-761:
     // every tile of the reference re-reads its halo the same way)
+    const unsigned long long epoch = g_stripEpoch.fetch_add(1) + 1;
+    static const unsigned long long timeoutMs = [] { const char* e = getenv("SSIM_CUDA_EXCHANGE_TIMEOUT_MS"); return e ? (unsigned long long)atoll(e) : 2000ull; }();
     std::vector<GeneralJob> jobs(n);
-    std::vector<bool> active(n, false);
     for (int g = 0; g < n; ++g) {
         const uint32_t y0 = (uint32_t)((uint64_t)H * g / n), y1 = (uint32_t)((uint64_t)H * (g + 1) / n);
-        CU_TRY(cudaSetDevice(devices[g]));
+        DEVICE_GUARD(devices[g]);
         int rc = ctx[g]->scalars.ensure(16);
-        if (rc) return rc;
-        if (y1 == y0) { CU_TRY(cudaMemsetAsync(ctx[g]->scalars.ptr, 0, 16, ctx[g]->stream)); continue; }
+        if (!rc) rc = ctx[g]->chunkSums.ensure(sizeof(double) * Context::kMaxChunks);
+        if (!rc) rc = ctx[g]->chunkSumsHost.ensure(sizeof(double) * Context::kMaxChunks);
+        if (rc) return fail_all(rc);
+        ssimk::ExchangeParams x;
+        memset(&x, 0, sizeof(x));
+        if (n > 1 && !useNccl) {
+            for (int r = 0; r < n; ++r) x.peers[r] = (ssimk::ExchangeSlot*)xbuf[r];
+            x.world = n; x.rank = g; x.epoch = epoch; x.timeoutNs = timeoutMs * 1000000ull;
+            x.sumAll = (double*)ctx[g]->chunkSums.ptr;
+            x.status = (int*)((char*)ctx[g]->chunkSums.ptr + 8);
+            x.invCountAll = 0.0;
+        }
         const uint32_t s0 = y0 >= (uint32_t)ssimk::kHalo ? y0 - ssimk::kHalo : 0, s1 = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
         rc = enqueue_general(ctx[g], W, s1 - s0, y0 - s0, y1 - y0, a + (ptrdiff_t)s0 * strideA, stepA, strideA, b + (ptrdiff_t)s0 * strideB,
-                             stepB, strideB, map ? map + (ptrdiff_t)y0 * mapStride : nullptr, mapStep, mapStride, false, &jobs[g]);
-        if (rc) return rc;
-        active[g] = true;
+                             stepB, strideB, map ? map + (ptrdiff_t)y0 * mapStride : nullptr, mapStep, mapStride, false, &jobs[g], false, 1,
+                             x.world ? &x : nullptr);
+        if (rc) return fail_all(rc);
     }
-    if (n > 1) {
-        NCCL_TRY(g_nccl.GroupStart());
+    // where the total ends up on device 0: the exchange wrote it (and a status word) to chunkSums, NCCL reduces scalars in place
+    const void* dTotal = ctx[0]->scalars.ptr;
+    if (n > 1 && useNccl) {
+        if (g_nccl.GroupStart() != ncclSuccess) return fail_all(fail(EIO, "ncclGroupStart failed"));
         for (int g = 0; g < n; ++g)
-            NCCL_TRY(g_nccl.AllReduce(ctx[g]->scalars.ptr, ctx[g]->scalars.ptr, 1, ncclDouble, ncclSum, (*comms)[g], ctx[g]->stream));
-        NCCL_TRY(g_nccl.GroupEnd());
+            if (g_nccl.AllReduce(ctx[g]->scalars.ptr, ctx[g]->scalars.ptr, 1, ncclDouble, ncclSum, (*comms)[g], ctx[g]->stream) != ncclSuccess)
+                return fail_all(fail(EIO, "ncclAllReduce failed"));
+        if (g_nccl.GroupEnd() != ncclSuccess) return fail_all(fail(EIO, "ncclGroupEnd failed"));
+    } else if (n > 1) {
+        dTotal = ctx[0]->chunkSums.ptr;
     }
-    double total = 0.0;
-    CU_TRY(cudaSetDevice(devices[0]));
-    CU_TRY(cudaMemcpyAsync(&total, ctx[0]->scalars.ptr, sizeof(double), cudaMemcpyDeviceToHost, ctx[0]->stream));
+    {
+        DEVICE_GUARD(devices[0]);
+        if (cudaMemcpyAsync(ctx[0]->chunkSumsHost.ptr, dTotal, 16, cudaMemcpyDeviceToHost, ctx[0]->stream) != cudaSuccess)
+            return fail_all(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(total)"));
+    }
     for (int g = 0; g < n; ++g) {
-        if (active[g]) { int rc = finish_general(jobs[g]); if (rc) return rc; }
-        else { CU_TRY(cudaSetDevice(devices[g])); CU_TRY(cudaStreamSynchronize(ctx[g]->stream)); }
+        int rc = finish_general(jobs[g]);
+        if (rc) return fail_all(rc);
     }
+    const double total = *(const double*)ctx[0]->chunkSumsHost.ptr;
+    if (n > 1 && !useNccl && *(const int*)((const char*)ctx[0]->chunkSumsHost.ptr + 8) != 0)
+        return fail(EIO, "strip-sum exchange timed out: a peer GPU did not deliver its sum within %llu ms", timeoutMs);
     if (ssim) *ssim = (float)(total / (double)(uint32_t)(W * H));
     return 0;
 }
+
+int compute_channels_body(Context* c, uint32_t width, uint32_t height, uint32_t channels, const uint8_t* a, ptrdiff_t strideA,
+                          const uint8_t* b, ptrdiff_t strideB, float* map, ptrdiff_t mapStride, float* ssim);
 
 }  // namespace
 
@@ -794,11 +961,17 @@ int ssim_cuda_init(int device)
 void ssim_cuda_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_ctxMutex);
+    for (int d = 0; d < kFastDevices; ++d) g_ctxFast[d].store(nullptr, std::memory_order_release);
     for (auto& kv : g_ctx) destroy_context(kv.second);
     for (auto& kv : g_hostCtx)
         for (Context* s : kv.second) destroy_context(s);
     g_hostCtx.clear();
     g_ctx.clear();
+    {
+        std::lock_guard<std::mutex> xlock(g_xchgMutex);
+        for (auto& kv : g_xchgBuf) { DeviceGuard g(kv.first); cudaFree(kv.second); }
+        g_xchgBuf.clear();
+    }
     {
         std::lock_guard<std::mutex> nlock(g_nccl.mutex);
         for (auto& kv : g_nccl.comms)
@@ -843,12 +1016,8 @@ int ssim_cuda_compute_luma(int device, uint32_t width, uint32_t height, const ui
     if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
     GeneralJob job;
     rc = enqueue_general(c, width, height, 0, height, rgbA, stepA, strideA, rgbB, stepB, strideB, map, mapStep, mapStride, ssim != nullptr, &job, true);
-    if (rc) return rc;
-    float hostSsim = 0.f;
-    if (ssim) CU_TRY(cudaMemcpyAsync(&hostSsim, (char*)c->scalars.ptr + 8, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = finish_general(job))) return rc;
-    if (ssim) *ssim = hostSsim;
-    return 0;
+    if (rc) return drained(c, rc);
+    return finish_with_scalar(c, job, ssim);
 }
 
 int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint32_t channels, const uint8_t* a, ptrdiff_t strideA,
@@ -865,7 +1034,18 @@ int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint
     if (rc) return rc;
     std::unique_lock<std::mutex> lock;
     if (int arc = acquire_host_context(&c, &lock)) return arc;      // may switch to a free sibling context
-    CU_TRY(cudaSetDevice(device));
+    return drained(c, compute_channels_body(c, width, height, channels, a, strideA, b, strideB, map, mapStride, ssim));
+}
+
+}  // extern "C"
+
+namespace {
+int compute_channels_body(Context* c, uint32_t width, uint32_t height, uint32_t channels, const uint8_t* a, ptrdiff_t strideA,
+                          const uint8_t* b, ptrdiff_t strideB, float* map, ptrdiff_t mapStride, float* ssim)
+{
+    const size_t rowBytes = (size_t)width * channels;
+    int rc;
+    DEVICE_GUARD(c->device);
     cudaStream_t s = c->stream;
     const size_t rawPitch = align_up(rowBytes, 16), pitch = align_up(width, 16), plane = pitch * height;
     const size_t mapPitch = align_up(width, 4), mapPlane = mapPitch * height;
@@ -899,6 +1079,9 @@ int ssim_cuda_compute_channels(int device, uint32_t width, uint32_t height, uint
     if (ssim) memcpy(ssim, hostSsim, sizeof(float) * channels);
     return 0;
 }
+}  // namespace
+
+extern "C" {
 
 int ssim_cuda_compute_device(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows, uint32_t frames,
                              const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB, size_t frameStrideB,
@@ -907,7 +1090,7 @@ int ssim_cuda_compute_device(int device, void* stream, uint32_t width, uint32_t 
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, frames, dA, pitchA, frameStrideA, dB, pitchB,
                                frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim);
 }
@@ -932,9 +1115,9 @@ int ssim_cuda_compute_device_u16(int device, void* stream, uint32_t width, uint3
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, frames, (const uint8_t*)dA, pitchA, frameStrideA,
-                               (const uint8_t*)dB, pitchB, frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim, nullptr, 2);
+                               (const uint8_t*)dB, pitchB, frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim, 2);
 }
 
 // ---- strip sums exchanged over peer memory (NVLink) inside the reduction kernel
@@ -944,13 +1127,10 @@ int ssim_cuda_exchange_create(int device, void** dBuf, void* ipcHandle64)
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(device));
-    const size_t bytes = 2 * ssimk::kMaxRanks * sizeof(ssimk::ExchangeSlot);
-    CU_TRY(cudaMalloc(dBuf, bytes));
-    CU_TRY(cudaMemset(*dBuf, 0, bytes));
-    CU_TRY(cudaDeviceSynchronize());
+    if ((rc = exchange_alloc(device, dBuf))) return rc;
     if (ipcHandle64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        DEVICE_GUARD(device);
         cudaIpcMemHandle_t h;
         CU_TRY(cudaIpcGetMemHandle(&h, *dBuf));
         memcpy(ipcHandle64, &h, sizeof(h));
@@ -964,7 +1144,7 @@ int ssim_cuda_exchange_open(int device, const void* ipcHandle64, void** dPeerBuf
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     cudaIpcMemHandle_t h;
     memcpy(&h, ipcHandle64, sizeof(h));
     CU_TRY(cudaIpcOpenMemHandle(dPeerBuf, h, cudaIpcMemLazyEnablePeerAccess));
@@ -973,30 +1153,19 @@ int ssim_cuda_exchange_open(int device, const void* ipcHandle64, void** dPeerBuf
 
 int ssim_cuda_exchange_close(int device, void* dPeerBuf)
 {
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     CU_TRY(cudaIpcCloseMemHandle(dPeerBuf));
     return 0;
 }
 
 int ssim_cuda_exchange_destroy(int device, void* dBuf)
 {
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     CU_TRY(cudaFree(dBuf));
     return 0;
 }
 
-int ssim_cuda_exchange_enable_peer(int device, int peerDevice)
-{
-    if (device == peerDevice) return 0;
-    CU_TRY(cudaSetDevice(device));
-    int can = 0;
-    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peerDevice));
-    if (!can) return fail(ENODEV, "device %d cannot access device %d", device, peerDevice);
-    cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
-    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
-    CU_TRY(e);
-    return 0;
-}
+int ssim_cuda_exchange_enable_peer(int device, int peerDevice) { return enable_peer(device, peerDevice); }
 
 int ssim_cuda_compute_strip_allreduce(int device, void* stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
                                       uint32_t imageRows, const uint8_t* dA, size_t pitchA, const uint8_t* dB, size_t pitchB,
@@ -1010,7 +1179,7 @@ int ssim_cuda_compute_strip_allreduce(int device, void* stream, uint32_t width, 
     Context* c;
     int rc = get_context(device, &c);
     if (rc) return rc;
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     ssimk::ExchangeParams x;
     memset(&x, 0, sizeof(x));
     for (int r = 0; r < world; ++r) x.peers[r] = (ssimk::ExchangeSlot*)peerBufs[r];
@@ -1020,7 +1189,7 @@ int ssim_cuda_compute_strip_allreduce(int device, void* stream, uint32_t width, 
     x.sumAll = dSumAll; x.ssimAll = dSsimAll; x.status = dStatus;
     x.invCountAll = 1.0 / (double)(uint32_t)(width * imageRows);       // uint32 product, as src/ssim.cpp:1102
     return compute_device_impl(c, (cudaStream_t)stream, width, srcRows, outY0, outRows, 1, dA, pitchA, 0, dB, pitchB, 0, dMap, mapPitch, 0,
-                               nullptr, nullptr, nullptr, 1, &x);
+                               nullptr, nullptr, 1, &x);
 }
 
 int ssim_cuda_last_launch_count(void) { return g_lastLaunches; }
@@ -1043,11 +1212,15 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
     int rc = get_context(device, &c);
     if (rc) return rc;
     if (!dA || !dB || width == 0 || rows == 0) return fail(EINVAL, "bad synth_fill arguments");
-    CU_TRY(cudaSetDevice(device));
+    DEVICE_GUARD(device);
     CU_TRY(ssimk::launch_synth_fill((cudaStream_t)stream, dA, (long long)pitchA, dB, (long long)pitchB, (int)width, (int)rows, (int)y0, frame, seed));
     return 0;
 }
 
-void ssim_cuda_set_segment_rows(int rows) { g_segRowsOverride = rows > 0 ? rows : 0; }
+void ssim_cuda_set_tuning(int maxCtasPerSm, int minSlotRows)
+{
+    g_maxCtasPerSm.store(maxCtasPerSm > 0 ? maxCtasPerSm : 0, std::memory_order_relaxed);
+    g_minSlotRows.store(minSlotRows > 0 ? minSlotRows : 0, std::memory_order_relaxed);
+}
 
 }  // extern "C"

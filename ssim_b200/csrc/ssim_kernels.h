@@ -9,61 +9,167 @@
 namespace ssimk {
 
 // ---- geometry of the fused kernel (see DESIGN.md "Kernel")
-constexpr int kBandW       = 64;   // output columns per warp work item (lane owns columns lane and lane+32)
-constexpr int kBlkRows     = 8;    // rows per TMA block / horizontal-pass block
+constexpr int kBandW       = 64;   // output columns per work column ("band"; a consumer lane owns columns lane and lane+32)
+constexpr int kBlkRows     = 8;    // rows per TMA box = per horizontal-pass block = per ring unit
 constexpr int kHalo        = 5;    // Gaussian radius (reference src/ssim.cpp:227)
-constexpr int kBoxW        = 128;  // TMA box width in bytes: 16 left margin + 64 columns + right margin; 128 so that every box
-                                   // row lands on a 128-byte aligned shared-memory address (TMA needs that of the box start)
 constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row: the innermost TMA coordinate (bx - 16) must be
                                    // a multiple of 16 bytes -- measured on B200: x = -16 works, x = -8 raises "illegal instruction"
                                    // (tools/dev/tma_probe.cu)
 constexpr int kLoadRows    = 8;    // rows per TMA box (= one horizontal-pass block)
-constexpr int kStages      = 2;    // TMA ring depth per work item (the producer has slack; 3 stages would not fit 2 CTAs/SM)
-constexpr int kPairsPerCta = 4;    // work items per CTA: each is served by one producer warp and one consumer warp
+constexpr int kStages      = 2;    // TMA stages per warp pair
+constexpr int kPairsPerCta = 4;    // warp pairs per CTA: each is one producer warp and one consumer warp
 constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 256: warps 0-3 producers (TMA + horizontal pass), 4-7 consumers
+constexpr int kCtasPerSm   = 2;    // persistent grid: kCtasPerSm x numSMs CTAs, every one resident
 constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
 constexpr int kConsumerRegs = 160;
 constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partner warp's mbarrier
-constexpr int kImgStageBytes = kBoxW * kLoadRows;        // 1024
-constexpr int kStageBytes    = 2 * kImgStageBytes;       // 2048 (A then B)
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
 constexpr int kRingRowPad     = 32;                      // consecutive rows start 8 banks apart: see the ring layout in the kernel
 constexpr int kRingRowBytes   = 2 * kRingPlaneBytes + kRingRowPad;   // 1056: {E[a'], E[b']} plane, {E[(a'-b')^2], E[a'b']} plane, pad
+constexpr int kRingUnitBytes  = kBlkRows * kRingRowBytes;            // 8448: one producer block = one hand-over unit
 constexpr int kTaps           = 11;
-constexpr int kRingRows       = 2 * kTaps;               // 22: two halves of 11 rows; the consumer's unrolled body is 11 rows
-constexpr int kRingBytes      = kRingRows * kRingRowBytes; // 23232
-constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;  // 27392
-constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;       // 109568 -> 2 CTAs (16 warps) per SM
+constexpr int kBarsPerPair    = 16;                      // mbarriers per pair (128 bytes): tmaFull[2] stageEmpty[2] ringFull[4] ringEmpty[4]
 
-// Per pixel type geometry of the TMA stage (the ring and everything after the widening are identical).  16-bit pixels
-// (the extension the reference's README names): box rows of 80 elements = 160 bytes -- band column 0 sits
-// at byte 16 in both layouts, the innermost TMA coordinate bx-8 elements is again a multiple of 16 bytes, and since a
-// stage is one box only its start has to be 128-byte aligned.
+// Per pixel type geometry of the TMA stage and the depth of the ring (everything after the widening is identical).
+//   8-bit : box rows of 96 bytes = 16 left margin + 64 columns + 16 right margin; a stage (8 rows of A, 8 rows of B) is 1536
+//           bytes; the ring holds 3 units of 8 rows.
+//   16-bit: box rows of 80 elements = 160 bytes (band column 0 again at byte 16, x coordinate bx-8 elements = 16 bytes
+//           aligned); a stage is 2560 bytes, the ring holds 2 units (3 would not leave room for 8 pairs per SM).
+// Only the start of a box must be 128-byte aligned in shared memory (measured, tools/dev/tma_probe.cu): 8 x 96 = 768 and
+// 8 x 160 = 1280 both are multiples of 128, so A and B boxes follow each other without padding.
 template <bool kU16> struct PixGeo {
     static constexpr int kPixBytes      = kU16 ? 2 : 1;
-    static constexpr int kBoxBytes      = kU16 ? 160 : kBoxW;
-    static constexpr int kBoxElems      = kBoxBytes / kPixBytes;            // 128 / 80
+    static constexpr int kBoxBytes      = kU16 ? 160 : 96;
+    static constexpr int kBoxElems      = kBoxBytes / kPixBytes;            // 96 / 80
     static constexpr int kBoxLeftElems  = kBoxLeft / kPixBytes;             // 16 / 8
-    static constexpr int kImgStageBytes = kBoxBytes * kLoadRows;            // 1024 / 1280
-    static constexpr int kStageBytes    = 2 * kImgStageBytes;               // 2048 / 2560
-    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 27392 / 28416
-    static constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;    // 109568 / 113664 (2 CTAs/SM either way)
+    static constexpr int kImgStageBytes = kBoxBytes * kLoadRows;            // 768 / 1280
+    static constexpr int kStageBytes    = 2 * kImgStageBytes;               // 1536 / 2560
+    static constexpr int kRingUnits     = kU16 ? 2 : 3;
+    static constexpr int kRingRows      = kRingUnits * kBlkRows;            // 24 / 16
+    static constexpr int kRingBytes     = kRingUnits * kRingUnitBytes;      // 25344 / 16896
+    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 28416 / 22016
+    static constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;    // 113664 / 88064 (2 CTAs per SM either way)
 };
+
+// ---- work partition --------------------------------------------------------------------------------------------------
+// The kernel is persistent: `slots` warp pairs (at most kCtasPerSm x numSMs x kPairsPerCta, all resident at once) share
+// the work evenly and statically.  The work is laid out as one line: a COLUMN is one 64-pixel band of one frame
+// (cols = frames x bands, frame-major), every column is `outRows` rows long and is preceded by kPad = 2*kHalo "padding"
+// units that stand for the cost of starting a piece (the 10 extra input rows the vertical filter needs before its first
+// output).  Slot s owns the units [s*Q + min(s,R), ...) of that line (Q, R = quotient and remainder of units / slots), i.e.
+// every slot owns the same number of units +-1; the rows of a column that fall into a slot's range form a PIECE, which is
+// what a warp pair processes in one go (own halo above and below, replicated rows at the plane's edges).  A slot whose
+// range starts inside a column pays its own 10-row start-up, a range that crosses into the next column pays that
+// column's padding units: either way cost = units + 10 for every slot, so all pairs finish together -- no tail, and no
+// halo paid more often than once per slot and once per column.
+constexpr int kPad = 2 * kHalo;
+
+struct SlotPlan {
+    uint32_t slots;          // warp pairs that get work (<= maxSlots)
+    uint32_t shareQ, shareR; // units per slot: slot s owns shareQ + (s < shareR) units
+    uint32_t colUnits;       // units per column = outRows + kPad
+    uint32_t entries;        // partial-sum entries per slot = max number of frames whose units one slot can own
+};
+
+// Pure host logic (unit-tested on the CPU: tests/clients/plan_check.cpp).  minUnits: do not spread the work thinner than
+// this many units per slot (tiny images would otherwise pay 10 start-up rows for a handful of output rows per slot).
+inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint32_t frames, uint32_t minUnits, SlotPlan* plan)
+{
+    const unsigned long long bands = ((unsigned long long)width + kBandW - 1) / kBandW;
+    const unsigned long long cols = bands * frames;
+    const unsigned long long colUnits = (unsigned long long)outRows + kPad;
+    const unsigned long long units = cols * colUnits;
+    if (maxSlots < 1 || width == 0 || outRows == 0 || frames == 0 || cols > 0x7fffffffull || units > 0x7fffffffull) return false;
+    if (minUnits < 1) minUnits = 1;
+    unsigned long long slots = units / minUnits;
+    if (slots > maxSlots) slots = maxSlots;
+    if (slots < 1) slots = 1;
+    plan->slots = (uint32_t)slots;
+    plan->shareQ = (uint32_t)(units / slots);
+    plan->shareR = (uint32_t)(units % slots);
+    plan->colUnits = (uint32_t)colUnits;
+    const unsigned long long frameUnits = bands * colUnits;
+    // a range of n units touches at most (n + frameUnits - 2) / frameUnits + 1 frames
+    unsigned long long entries = ((unsigned long long)plan->shareQ + 1 + frameUnits - 2) / frameUnits + 1;
+    if (entries > frames) entries = frames;
+    plan->entries = (uint32_t)entries;
+    return true;
+}
+
+// One piece: rows [r0, r0 + nOut) of column `col` (relative to the first output row of the call).
+struct Piece {
+    int frame, band;
+    int r0, nOut;
+};
+
+// Enumerates the pieces of a slot in order.  Used by both warps of a pair in the kernel (everything here is warp-uniform
+// integer arithmetic) and by the CPU tests; divisions go through fast_div() constants.
+struct PieceCursor {
+    uint32_t q, qEnd;        // next unit / end of the slot's range
+    uint32_t colBase;        // first unit of the current column
+    int frame, band;
+};
+
+#if defined(__CUDACC__)
+#define SSIMK_HD __host__ __device__ __forceinline__
+#else
+#define SSIMK_HD inline
+#endif
+
+SSIMK_HD uint32_t ssimk_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((unsigned long long)a * b) >> 32); }
+SSIMK_HD uint32_t ssimk_div(uint32_t n, uint32_t mul, uint32_t shift) { return mul ? ssimk_mulhi(n, mul) >> shift : n; }
+
+struct SlotGeo {             // the part of FusedParams the cursor needs (kept separate so that the CPU tests can build it)
+    uint32_t slots, shareQ, shareR, colUnits, bands;
+    uint32_t colMul, colShift;       // n / colUnits
+    uint32_t bandsMul, bandsShift;   // n / bands
+};
+
+SSIMK_HD void cursor_init(PieceCursor& c, const SlotGeo& g, uint32_t slot)
+{
+    c.q = slot * g.shareQ + (slot < g.shareR ? slot : g.shareR);
+    c.qEnd = c.q + g.shareQ + (slot < g.shareR ? 1u : 0u);
+    const uint32_t col = ssimk_div(c.q, g.colMul, g.colShift);
+    c.colBase = col * g.colUnits;
+    c.frame = (int)ssimk_div(col, g.bandsMul, g.bandsShift);
+    c.band = (int)(col - (uint32_t)c.frame * g.bands);
+}
+
+// next piece with at least one output row; false when the slot's range is exhausted
+SSIMK_HD bool cursor_next(PieceCursor& c, const SlotGeo& g, Piece& pc)
+{
+    while (c.q < c.qEnd) {
+        const uint32_t ua = c.q - c.colBase;                                          // first unit inside the column
+        const uint32_t ub = c.qEnd - c.colBase < g.colUnits ? c.qEnd - c.colBase : g.colUnits;
+        const int r0 = (int)(ua > (uint32_t)kPad ? ua - kPad : 0u);
+        const int r1 = (int)(ub > (uint32_t)kPad ? ub - kPad : 0u);
+        pc.frame = c.frame; pc.band = c.band; pc.r0 = r0; pc.nOut = r1 - r0;
+        c.colBase += g.colUnits;
+        c.q = c.colBase;
+        if (++c.band == (int)g.bands) { c.band = 0; ++c.frame; }
+        if (r1 > r0) return true;
+    }
+    return false;
+}
 
 struct FusedParams {
     int u16;                 // 0: 8-bit pixels, 1: 16-bit pixels (pitches and frame strides stay in BYTES)
-    const uint8_t* a;        // raw planes (used only to fetch the per-item centring pixel)
+    const uint8_t* a;        // raw planes (used only to fetch the per-piece centring pixel)
     const uint8_t* b;
     long long pitchA, frameStrideA, pitchB, frameStrideB;
     float*  map;             // NULL when no map is wanted
     long long mapPitch, mapFrameStride;   // floats
-    double* partials;        // [items] per-warp-item partial sums
     int width, srcRows, outY0, outRows, frames;
-    int bands, segs, segRows;
-    long long items;         // < 2^31 (checked by the host)
-    uint32_t bandsMul, bandsShift, segsMul, segsShift;   // n / d == umulhi(n, mul) >> shift for n < 2^31 (d == 1: mul == 0); see fast_div()
+    SlotGeo geo;
+    // reduction workspace (per stream): partial sums [slots][entries] (entry e of slot s belongs to frame
+    // e + the first frame whose units s owns) and one arrival counter per frame
+    double*   partials;
+    unsigned* frameDone;     // [frames], zero before the launch; the last slot to arrive at a frame reduces it and resets it
+    uint32_t  entries;
+    double*   sums;          // out, may be NULL: [frames] sum of the SSIM values of each frame
+    float*    ssim;          // out, may be NULL: [frames] float(sum * invCount)
+    double    invCount;      // 1 / double(uint32(width*outRows))
     float g[6];              // separable 11-tap weights: g[d] is the tap at distance d from the centre
-    float c1, c2;
     uint32_t magic;          // 0x4B000000 (float 2^23): kept opaque to ptxas, see the kernel
     uint32_t backoffNs;      // sleep between polls of the partner warp's mbarrier
     float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
@@ -81,58 +187,21 @@ inline void fast_div(uint32_t d, uint32_t* mul, uint32_t* shift)
     *shift = L - 1;
 }
 
-// Work partition (pure host logic, unit-tested on the CPU: tests/clients/plan_check.cpp).  A work item is (frame, row
-// segment, 64-column band).  The number of segments per frame decides both the halo overhead (10 extra input rows per
-// segment) and how full the last wave of CTAs is.  Measured on B200 (tools/dev/batch_sweep.py, strip_sweep.py): 64 x 4K
-// with 720-row segments = 9.73 waves 240.8k Mpix/s, 540-row = 12.97 waves 248.4k; a 16384 x 2058 strip with 515-row
-// segments (0.86 waves) 187 us, 229-row (1.95 waves) 169 us.  Pick the count that minimises
-//     waves x (rows + halo + per-item set-up),
-// a last wave that fills at most half the CTA slots counting 0.4-0.7 (its CTAs have an SM to themselves and run faster);
-// the candidates stop where a segment would drop below 24 rows.  overrideRows > 0 forces that many rows per segment.
-inline void plan_segments(long long ctaSlots, uint32_t width, uint32_t outRows, uint32_t frames, int overrideRows, int* segRows, int* segs)
+inline SlotGeo make_slot_geo(const SlotPlan& plan, uint32_t width)
 {
-    const long long bands = ((long long)width + kBandW - 1) / kBandW;
-    const long long units = bands * frames;
-    long long s = 1;
-    if (overrideRows > 0) {
-        s = ((long long)outRows + overrideRows - 1) / overrideRows;
-    } else {
-        long long maxSegs = outRows / 24;
-        if (maxSegs > 256) maxSegs = 256;
-        if (maxSegs < 1) maxSegs = 1;
-        if (ctaSlots < 1) ctaSlots = 1;
-        double best = 0;
-        for (long long cand = 1; cand <= maxSegs; ++cand) {
-            const long long rows = ((long long)outRows + cand - 1) / cand;
-            const long long nseg = ((long long)outRows + rows - 1) / rows;
-            if (nseg != cand && cand != 1) continue;                    // same partition as a smaller candidate
-            const long long ctas = (units * nseg + kPairsPerCta - 1) / kPairsPerCta;
-            const long long full = ctas / ctaSlots, rem = ctas % ctaSlots;
-            double tail = 0.0;
-            if (rem > 0) tail = 2 * rem > ctaSlots ? 1.0 : 0.4 + 0.3 * (double)(2 * rem) / (double)ctaSlots;
-            const double cost = ((double)full + tail) * (double)(rows + 2 * kHalo + 12);
-            if (cand == 1 || cost < best) { best = cost; s = cand; }
-        }
-    }
-    if (s > (long long)outRows) s = outRows;
-    if (s < 1) s = 1;
-    const int rows = (int)(((long long)outRows + s - 1) / s);
-    *segRows = rows;
-    *segs = (int)(((long long)outRows + rows - 1) / rows);
+    SlotGeo g;
+    g.slots = plan.slots; g.shareQ = plan.shareQ; g.shareR = plan.shareR; g.colUnits = plan.colUnits;
+    g.bands = (width + kBandW - 1) / kBandW;
+    fast_div(g.colUnits, &g.colMul, &g.colShift);
+    fast_div(g.bands, &g.bandsMul, &g.bandsShift);
+    return g;
 }
 
-struct FinalizeParams {
-    const double* partials;
-    double* sums;            // may be NULL
-    float*  ssim;            // may be NULL
-    int itemsPerFrame;
-    double invCount;         // 1 / double(uint32(width*outRows))
-};
-
-// Cross-GPU sum fused into the reduction kernel (strips of one image): every rank owns an exchange buffer of
-// 2 x kMaxRanks slots; the reduction kernel of rank r stores its partial sum straight into slot [epoch & 1][r] of EVERY
-// peer's buffer (NVLink peer stores, value then epoch with release semantics at system scope), then waits until its own
-// buffer holds all `world` slots of this epoch and adds them up in rank order (deterministic, identical on every rank).
+// Cross-GPU sum fused into the kernel (strips of one image): every rank owns an exchange buffer of
+// 2 x kMaxRanks slots; the last consumer warp of rank r's kernel, after reducing the strip, stores the strip sum straight into
+// slot [epoch & 1][r] of EVERY peer's buffer (NVLink peer stores, value then epoch with release semantics at system scope), then
+// waits until its own buffer holds all `world` slots of this epoch and adds them up in rank order (deterministic, identical
+// on every rank).  world == 0: no exchange.
 constexpr int kMaxRanks = 16;
 struct ExchangeSlot { double value; unsigned long long epoch; };
 struct ExchangeParams {
@@ -145,10 +214,10 @@ struct ExchangeParams {
     double invCountAll;
     int* status;                      // out: 0 ok, 1 timed out
 };
-cudaError_t launch_finalize_allreduce(cudaStream_t stream, const FinalizeParams& p, const ExchangeParams& x);
 
-cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p);
-cudaError_t launch_finalize(cudaStream_t stream, const FinalizeParams& p, int frames);
+// ONE launch per call: TMA loads, both filter passes, the formula, the map, the per-frame reduction and (xchg != NULL) the
+// cross-GPU sum.  The grid is ceil(p.geo.slots / kPairsPerCta) CTAs, all resident.
+cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams* xchg);
 // per-device preparation (sets the dynamic shared-memory limit on the CURRENT device) + kernel facts
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm);
 

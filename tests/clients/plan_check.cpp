@@ -1,37 +1,75 @@
-// Host-only check of ssimk::plan_segments(): the partition must cover every output row exactly once with non-empty
-// segments for any shape, and reproduce the choices the measurements in DESIGN.md were taken with.
+// Host-only check of the persistent kernel's work partition (ssimk::plan_slots + the PieceCursor both warps of a pair
+// run in the kernel): for any shape the pieces of all slots must tile every column's rows exactly once, in order, with
+// pieces of the same slot in increasing (frame, band) order, shares balanced to +-1 unit, and no slot touching more frames
+// than the plan reserved partial-sum entries for.
 #include <cstdint>
 #include <cstdio>
+#include <vector>
 #include "ssim_kernels.h"
 
 static int fails = 0;
-static void expect(bool ok, const char* what, uint32_t w, uint32_t h, uint32_t f, int rows, int segs)
+static void expect(bool ok, const char* what, uint32_t w, uint32_t h, uint32_t f, uint32_t slots)
 {
-    if (!ok) { std::printf("FAIL %s: %ux%u x%u -> %d rows x %d segments\n", what, w, h, f, rows, segs); ++fails; }
+    if (!ok && fails < 20) std::printf("FAIL %s: %ux%u x%u on %u slots\n", what, w, h, f, slots);
+    if (!ok) ++fails;
+}
+
+static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_t minUnits)
+{
+    ssimk::SlotPlan plan;
+    if (!ssimk::plan_slots(maxSlots, w, h, f, minUnits, &plan)) { expect(false, "plan_slots refused", w, h, f, maxSlots); return; }
+    const ssimk::SlotGeo g = ssimk::make_slot_geo(plan, w);
+    const uint32_t bands = (w + 63) / 64;
+    const uint64_t cols = (uint64_t)bands * f;
+    expect(plan.slots >= 1 && plan.slots <= maxSlots, "slot count in range", w, h, f, plan.slots);
+    expect((uint64_t)plan.slots * plan.shareQ + plan.shareR == cols * (h + 10), "shares add up to all units", w, h, f, plan.slots);
+    expect(plan.shareQ >= (plan.slots > 1 ? minUnits : 1u), "no slot thinner than minUnits", w, h, f, plan.slots);
+    std::vector<uint32_t> nextRow(cols, 0);          // rows [0, nextRow) of each column are covered so far
+    uint64_t lastCol = 0;
+    bool first = true;
+    for (uint32_t s = 0; s < plan.slots; ++s) {
+        ssimk::PieceCursor c;
+        ssimk::cursor_init(c, g, s);
+        ssimk::Piece pc;
+        int framesTouched = 0, lastFrame = -1;
+        while (ssimk::cursor_next(c, g, pc)) {
+            const uint64_t col = (uint64_t)pc.frame * bands + pc.band;
+            expect(pc.frame >= 0 && (uint32_t)pc.frame < f && pc.band >= 0 && (uint32_t)pc.band < bands, "piece inside the batch", w, h, f, plan.slots);
+            if (col >= cols) return;
+            expect(pc.nOut >= 1 && (uint32_t)(pc.r0 + pc.nOut) <= h, "piece inside its column", w, h, f, plan.slots);
+            expect((uint32_t)pc.r0 == nextRow[col], "pieces of a column are contiguous and in order", w, h, f, plan.slots);
+            expect(first || col >= lastCol, "columns in increasing order across slots", w, h, f, plan.slots);
+            nextRow[col] = (uint32_t)(pc.r0 + pc.nOut);
+            lastCol = col; first = false;
+            if (pc.frame != lastFrame) { ++framesTouched; lastFrame = pc.frame; }
+        }
+        expect((uint32_t)framesTouched <= plan.entries, "entries cover every frame a slot touches", w, h, f, plan.slots);
+    }
+    for (uint64_t c = 0; c < cols; ++c) expect(nextRow[c] == h, "every row of every column covered exactly once", w, h, f, plan.slots);
 }
 
 int main()
 {
-    const long long slots = 148 * 2;          // B200: 148 SMs x 2 CTAs
+    const uint32_t slots = 148 * 2 * 4;          // B200: 148 SMs x 2 CTAs x 4 warp pairs
     const uint32_t widths[] = {1, 63, 64, 65, 640, 1920, 3840, 16384, 100000};
-    const uint32_t heights[] = {1, 2, 23, 24, 25, 47, 48, 141, 1080, 2058, 2160, 16384, 1000003};
-    const uint32_t frames[] = {1, 3, 64, 512, 4096};
+    const uint32_t heights[] = {1, 2, 9, 10, 11, 23, 24, 25, 47, 141, 1080, 2058, 2160, 16384};
+    const uint32_t frames[] = {1, 2, 3, 64, 512};
     for (uint32_t w : widths) for (uint32_t h : heights) for (uint32_t f : frames) {
-        int rows = 0, segs = 0;
-        ssimk::plan_segments(slots, w, h, f, 0, &rows, &segs);
-        expect(rows >= 1 && segs >= 1, "positive", w, h, f, rows, segs);
-        expect((long long)rows * segs >= h && (long long)rows * (segs - 1) < h, "covers every row exactly once, last segment not empty", w, h, f, rows, segs);
-        expect(h < 48 || rows >= 24, "segments of at least 24 rows", w, h, f, rows, segs);
-        for (int forced : {1, 7, 100, 5000}) {
-            ssimk::plan_segments(slots, w, h, f, forced, &rows, &segs);
-            expect((long long)rows * segs >= h && (long long)rows * (segs - 1) < h && rows <= (forced > (int)h ? (int)h : forced), "override", w, h, f, rows, segs);
-        }
+        if ((uint64_t)((w + 63) / 64) * f * (h + 10) > 40000000ull) continue;     // keep the check fast
+        check(slots, w, h, f, 24);
+        check(slots / 2, w, h, f, 1);
+        check(7, w, h, f, 100);
     }
-    int rows, segs;
-    ssimk::plan_segments(slots, 3840, 2160, 64, 0, &rows, &segs);   expect(rows == 540 && segs == 4, "64 x 4K: 12.97 waves", 3840, 2160, 64, rows, segs);
-    ssimk::plan_segments(slots, 3840, 2160, 1, 0, &rows, &segs);    expect(segs == 19, "one 4K pair: one wave of 285 CTAs", 3840, 2160, 1, rows, segs);
-    ssimk::plan_segments(slots, 16384, 2058, 1, 0, &rows, &segs);   expect(segs == 9, "16384 x 2058 strip: 1.95 waves", 16384, 2058, 1, rows, segs);
-    ssimk::plan_segments(slots, 1920, 1080, 1, 0, &rows, &segs);    expect(segs == 39, "one 1080p pair: one wave", 1920, 1080, 1, rows, segs);
-    std::printf(fails ? "plan_segments: %d failures\n" : "plan_segments ok\n", fails);
+    check(slots, 1920, 1080, 4096, 24);
+    check(slots, 64, 64, 4096, 24);
+    check(1, 3840, 2160, 2, 24);
+    // the documented plans
+    ssimk::SlotPlan p;
+    ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p);   expect(p.slots == 1184 && p.shareQ == 109 && p.entries == 1, "one 4K pair: 109-110 units per slot", 3840, 2160, 1, p.slots);
+    ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p);  expect(p.slots == 1184 && p.shareQ == 7037, "64 x 4K", 3840, 2160, 64, p.slots);
+    ssimk::plan_slots(slots, 333, 141, 1, 24, &p);     expect(p.slots == 37, "small image: fewer slots", 333, 141, 1, p.slots);
+    ssimk::plan_slots(slots, 8, 8, 1, 24, &p);         expect(p.slots == 1 && p.shareQ == 18, "tiny image: one slot", 8, 8, 1, p.slots);
+    expect(!ssimk::plan_slots(slots, 100000, 100000, 100, 24, &p), "more than 2^31 units is refused", 100000, 100000, 100, 0);
+    std::printf(fails ? "plan_slots: %d failures\n" : "plan_slots ok\n", fails);
     return fails ? 1 : 0;
 }

@@ -69,10 +69,26 @@ def main():
     png = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_360_07806.png")).convert("RGB"), dtype=np.uint8)
     jpg = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_360_07806_50.jpg")).convert("RGB"), dtype=np.uint8)
     assert png.shape == (360, 640, 3) and jpg.shape == png.shape
-    rows = 80  # keep the first 80 rows only (enough for the 65-row crop); stride stays 640*3
-    png, jpg = png[:rows].copy(), jpg[:rows].copy()
-    np.savez_compressed(os.path.join(OUT, "bbb360_top80.npz"), png=png, jpg50=jpg)
+    np.savez_compressed(os.path.join(OUT, "bbb360.npz"), png=png, jpg50=jpg)       # the full frames; tests slice the top 80 rows
     bbb = {}
+    # full frames, all three channels, and the 1080p frame (green channel only: fixture size), like the reference's
+    # tests/rmgr-ssim-tests.cpp:388-425 (whose hard-coded constants were made with stb_image's JPEG decoder, not libjpeg)
+    for ch in range(3):
+        kw = dict(step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, width=640, height=360, a_off=ch, b_off=ch)
+        r64a, m64a = oracle.ref_ssim("f64", jpg, png, want_map=True, **kw)
+        r32, _ = oracle.ref_ssim("f32", jpg, png, openmp=True, **kw)
+        bbb["640x360_ch%d" % ch] = {"ref_f64_auto": f32(r64a), "ref_f32_auto_openmp": f32(r32), "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum()),
+                                    "ref_f64_auto_map_min": f32(m64a.min())}
+    big_png = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_1080_07806.png")).convert("RGB"), dtype=np.uint8)[..., 1].copy()
+    big_jpg = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_1080_07806_50.jpg")).convert("RGB"), dtype=np.uint8)[..., 1].copy()
+    assert big_png.shape == (1080, 1920)
+    np.savez_compressed(os.path.join(OUT, "bbb1080_green.npz"), png=big_png, jpg50=big_jpg)
+    r64a, m64a = oracle.ref_ssim("f64", big_jpg, big_png, want_map=True)
+    r32, _ = oracle.ref_ssim("f32", big_jpg, big_png, openmp=True)
+    bbb["1920x1080_green"] = {"ref_f64_auto": f32(r64a), "ref_f32_auto_openmp": f32(r32), "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum()),
+                              "ref_f64_auto_map_min": f32(m64a.min())}
+    rows = 80  # the crops below use the first 80 rows only; stride stays 640*3
+    png, jpg = png[:rows].copy(), jpg[:rows].copy()
     for (w, h) in [(255, 63), (257, 65), (640, 80)]:
         for ch in range(3):
             kw = dict(step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, width=w, height=h, a_off=ch, b_off=ch)
@@ -103,8 +119,29 @@ def main():
         syn["%dx%d_f3" % (w, h)] = {"ref_f64_auto": f32(r64a), "ref_f64_generic": f32(r64g), "ref_f32_auto": f32(r32),
                                     "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum())}
 
+    # ---- 16-bit (L = 65535): the reference's own naive::compute_ssim<double, uint16_t> (tests/ssim_naive.h:230-339,
+    #      compiled in place into oracle/_ref/libnaive.so) on genuinely 16-bit inputs
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import u16_inputs  # noqa: E402
+    assert oracle.have_naive()
+    u16 = {}
+    for (h, w) in u16_inputs.U16_SHAPES:
+        a, b = u16_inputs.pair16(h, w, u16_inputs.seed_of(h, w))
+        mean, m = oracle.naive_ssim(a, b, want_map=True)
+        u16["%dx%d" % (w, h)] = {"inputs_sha256_16": u16_inputs.digest(a, b), "naive_double_mean": repr(mean),
+                                 "naive_map_sum": repr(float(m.sum())), "naive_map_min": repr(float(m.min()))}
+    h, w = u16_inputs.U16_FIXTURE_SHAPE
+    a, b = u16_inputs.pair16(h, w, 2024)
+    mean, m = oracle.naive_ssim(a, b, want_map=True)
+    np.savez_compressed(os.path.join(OUT, "u16_pair.npz"), a=a, b=b, naive_map=m.astype(np.float32))
+    u16["fixture_%dx%d" % (w, h)] = {"naive_double_mean": repr(mean)}
+    # the same shim, 8-bit instantiation, must reproduce the reference's einstein known answers (they were made with it)
+    for name, golden in EINSTEIN:
+        mean, _ = oracle.naive_ssim(planes[name], ref)
+        assert abs(mean - float(golden)) < 1e-13, (name, mean, golden)
+
     with open(os.path.join(OUT, "golden.json"), "w") as fh:
-        json.dump({"einstein": ein, "bbb360_jpg50": bbb, "synthetic": syn,
+        json.dump({"einstein": ein, "bbb360_jpg50": bbb, "synthetic": syn, "u16_naive": u16,
                    "note": "ref_* values are float32 results of the unmodified reference build (oracle/_ref), repr as double"},
                   fh, indent=1, sort_keys=True)
     print("wrote", OUT)

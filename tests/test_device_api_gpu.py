@@ -29,7 +29,7 @@ def test_batch_of_frames_matches_per_frame_oracle():
     api.compute_device(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, F, dA.data_ptr(), W, W * H, dB.data_ptr(), W, W * H,
                        dMap.data_ptr(), W, W * H, dSums.data_ptr(), dSsim.data_ptr())
     torch.cuda.synchronize()
-    assert api.cuda_lib().ssim_cuda_last_launch_count() == 2
+    assert api.cuda_lib().ssim_cuda_last_launch_count() == 1
     for f in range(F):
         o, tot, om = oracle.oracle_ssim(a[f], b[f], want_map=True)
         assert abs(float(dSsim[f]) - float(o)) <= GLOBAL_TOL
@@ -62,6 +62,80 @@ def test_strips_with_halo_rows_reproduce_the_full_image(world):
         total += float(dSum.item())
     assert abs(float(parallel.mean_from_partials(total, W, H)) - float(o)) <= GLOBAL_TOL
     assert np.abs(got_map - om).max() <= PIXEL_TOL
+
+
+@pytest.mark.parametrize("geom", [(7, 5, 2), (6, 5, 1), (7, 0, 7), (3, 1, 2), (9, 5, 4), (12, 5, 2)])
+def test_short_strips_clamp_rows_like_the_reference(geom):
+    """Strips of fewer than 8 source rows (a 10-row image over 8 GPUs has them): rows below the strip replicate its last
+    row (src/ssim.cpp:560-570), the TMA box being taller than the plane must not leak zero-filled rows."""
+    src_rows, oy, orows = geom
+    W = 200
+    a, b = synth_pair(W, src_rows, 9)
+    # the oracle on the same rows treats them as a whole image: its rows [oy, oy+orows) see the same clamped neighbours
+    o, tot, om = oracle.oracle_ssim(a, b, want_map=True)
+    pitch = 208
+    dA = torch.zeros((src_rows, pitch), dtype=torch.uint8, device="cuda"); dB = torch.zeros_like(dA)
+    dA[:, :W] = _dev(a); dB[:, :W] = _dev(b)
+    dMap = torch.zeros((orows, W), dtype=torch.float32, device="cuda")
+    dSum = torch.zeros(1, dtype=torch.float64, device="cuda")
+    api.compute_device(0, None, W, src_rows, oy, orows, 1, dA.data_ptr(), pitch, 0, dB.data_ptr(), pitch, 0, dMap.data_ptr(), W, 0, dSum.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert np.abs(dMap.cpu().numpy() - om[oy:oy + orows]).max() <= PIXEL_TOL
+    assert abs(float(dSum.item()) - float(om[oy:oy + orows].astype(np.float64).sum())) <= 1e-4 * W * orows
+
+
+@pytest.mark.parametrize("shape", [(37, 208, 77), (64, 64, 64), (130, 1280, 33), (300, 48, 20)])
+def test_many_frames_are_reduced_per_frame(shape):
+    """More frames than warp pairs, frames smaller than a slot's share, slots spanning several frames: every frame's sum must
+    come out of the in-kernel per-frame reduction exactly once (and the arrival counters must be left clean for the next
+    launch, which the second round checks)."""
+    F, W, H = shape
+    a = np.stack([synth_pair(W, H, f)[0] for f in range(F)])
+    b = np.stack([synth_pair(W, H, f)[1] for f in range(F)])
+    dA, dB = _dev(a), _dev(b)
+    dSums = torch.zeros(F, dtype=torch.float64, device="cuda")
+    dSsim = torch.zeros(F, dtype=torch.float32, device="cuda")
+    dMap = torch.zeros((F, H, W), dtype=torch.float32, device="cuda")
+    for rnd in range(2):
+        dSums.zero_(); dSsim.zero_()
+        api.compute_device(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, F, dA.data_ptr(), W, W * H, dB.data_ptr(), W, W * H,
+                           dMap.data_ptr() if rnd == 0 else None, W, W * H, dSums.data_ptr(), dSsim.data_ptr())
+        torch.cuda.synchronize()
+        maps = dMap.cpu().numpy().astype(np.float64).sum(axis=(1, 2))
+        assert np.abs(dSums.cpu().numpy() - maps).max() <= 1e-5 * W * H          # sums == sums of the stored maps
+        for f in (0, 1, F // 2, F - 1):
+            o, tot, _ = oracle.oracle_ssim(a[f], b[f])
+            assert abs(float(dSsim[f]) - float(o)) <= GLOBAL_TOL, (f, rnd)
+
+
+def test_tuning_knobs_do_not_change_results():
+    """ssim_cuda_set_tuning: any slot count gives the same map values up to the per-piece centring (different pieces, same math)"""
+    W, H = 640, 360
+    a, b = synth_pair(W, H, 12)
+    o, _, om = oracle.oracle_ssim(a, b, want_map=True)
+    lib = api.cuda_lib()
+    try:
+        for ctas, rows in ((1, 0), (2, 200), (1, 5000), (0, 1), (0, 0)):
+            lib.ssim_cuda_set_tuning(ctas, rows)
+            s, m = api.compute_ssim(a, b, want_map=True)
+            assert abs(float(s) - float(o)) <= GLOBAL_TOL and np.abs(m - om).max() <= PIXEL_TOL, (ctas, rows)
+    finally:
+        lib.ssim_cuda_set_tuning(0, 0)
+
+
+def test_current_device_is_left_alone():
+    """entry points make their device current only for the duration of the call"""
+    if api.cuda_lib().ssim_cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    torch.cuda.set_device(1)
+    try:
+        a, b = synth_pair(300, 100, 1)
+        api.compute_ssim(a, b)                                  # SSIM_CUDA_DEVICE unset -> device 0
+        assert torch.cuda.current_device() == 1
+        x = torch.ones(8, device="cuda")
+        assert x.device.index == 1
+    finally:
+        torch.cuda.set_device(0)
 
 
 def test_compute_strips_entry_point():

@@ -35,7 +35,7 @@ def test_libssim_cuda_exports_every_declared_symbol():
     assert len(names) >= 12
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.ssim_cuda_abi_version() == 1
+    assert lib.ssim_cuda_abi_version() == 2
     assert lib.ssim_cuda_last_error_string() is not None
 
 
@@ -165,7 +165,7 @@ def test_two_rank_gloo_strips_and_batch(tmp_path):
 @pytest.mark.parametrize("name", ["fast_div_check", "plan_check"])
 def test_host_side_kernel_helpers(tmp_path, name):
     """Host-only logic that lives in ssim_kernels.h, compiled as plain C++: fast_div() (the kernel's work-item decode) against
-    plain division, plan_segments() (rows per work item) for coverage invariants and the documented choices."""
+    plain division, plan_slots() + the PieceCursor (the persistent kernel's work partition) for coverage invariants and the documented plans."""
     exe = str(tmp_path / name)
     src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "clients", name + ".cpp")
     inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ssim_b200", "csrc")

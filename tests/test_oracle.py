@@ -143,8 +143,8 @@ def test_reference_builds_are_what_they_claim():
 
 
 def test_u16_oracle_scale_invariance():
-    """The 16-bit restatement (L = 65535; not implemented by the reference, README.md:107-111) is pinned through
-    SSIM_16(257 a, 257 b) == SSIM_8(a, b): C1 and C2 scale with L^2 and 65535 = 257 * 255."""
+    """Scale invariance of the 16-bit restatement (L = 65535): SSIM_16(257 a, 257 b) == SSIM_8(a, b), because C1 and C2 scale
+    with L^2 and 65535 = 257 * 255.  (The pin to the reference's own 16-bit template is further down.)"""
     from oracle import oracle_ssim, oracle_ssim_u16
     rng = np.random.default_rng(3)
     for h, w in ((1, 1), (7, 19), (97, 131)):
@@ -161,3 +161,49 @@ def test_u16_oracle_scale_invariance():
     sba, _, _ = oracle_ssim_u16(b, a)
     saa, _, maa = oracle_ssim_u16(a, a.copy(), want_map=True)
     assert sab == sba and saa == np.float32(1.0) and (maa == 1.0).all() and sab < 1.0
+
+
+# ---- 16-bit pinned to the reference's own naive::compute_ssim<double, uint16_t> (tests/ssim_naive.h:230-339)
+import u16_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("shape", u16_inputs.U16_SHAPES)
+def test_u16_oracle_matches_reference_naive_vectors(shape, golden):
+    """Committed vectors: what oracle/_ref/libnaive.so (the reference's template, T = uint16_t => L = 65535) returned for
+    genuinely 16-bit inputs; the restatement with true-math taps must agree to 1e-12 on the double mean."""
+    h, w = shape
+    a, b = u16_inputs.pair16(h, w, u16_inputs.seed_of(h, w))
+    g = golden["u16_naive"]["%dx%d" % (w, h)]
+    assert u16_inputs.digest(a, b) == g["inputs_sha256_16"], "numpy's generator no longer reproduces the recorded inputs"
+    _, total, m = oracle.oracle_ssim_u16(a, b, want_map=True, taps=oracle.TAPS_RUNTIME)
+    assert abs(total / (w * h) - float(g["naive_double_mean"])) <= 1e-12
+    assert abs(float(m.min()) - float(g["naive_map_min"])) <= 1e-6            # the oracle's map is float32
+    # the gating oracle mode (float-pipeline window, as every shipped reference build applies it) stays within the
+    # window's normalisation bias of the true-math one
+    s_tab, _, _ = oracle.oracle_ssim_u16(a, b, taps=oracle.TAPS_TABLE)
+    assert abs(float(s_tab) - float(g["naive_double_mean"])) <= 2e-6
+
+
+def test_u16_oracle_matches_reference_naive_map_fixture(golden):
+    d = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "u16_pair.npz"))
+    a, b, nm = d["a"], d["b"], d["naive_map"]
+    assert a.dtype == np.uint16 and int(a.max()) > 255                          # genuinely 16-bit content
+    h, w = a.shape
+    _, total, m = oracle.oracle_ssim_u16(a, b, want_map=True, taps=oracle.TAPS_RUNTIME)
+    assert abs(total / (w * h) - float(golden["u16_naive"]["fixture_%dx%d" % (w, h)]["naive_double_mean"])) <= 1e-12
+    assert np.abs(m - nm).max() <= 2e-7                                         # both maps rounded to float32
+
+
+@pytest.mark.skipif(not oracle.have_naive(), reason="oracle/_ref/libnaive.so not built (needs /root/reference once)")
+def test_u16_and_u8_oracle_live_against_reference_naive():
+    rng = np.random.default_rng(11)
+    for h, w in ((5, 9), (64, 64), (70, 131)):
+        a = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+        b = np.clip(a.astype(int) + rng.integers(-5000, 5001, a.shape), 0, 65535).astype(np.uint16)
+        mean, nm = oracle.naive_ssim(a, b, want_map=True)
+        _, total, m = oracle.oracle_ssim_u16(a, b, want_map=True, taps=oracle.TAPS_RUNTIME)
+        assert abs(total / (w * h) - mean) <= 1e-12 and np.abs(m - nm.astype(np.float32)).max() <= 2e-7
+        a8, b8 = (a >> 8).astype(np.uint8), (b >> 8).astype(np.uint8)
+        mean8, _ = oracle.naive_ssim(a8, b8)
+        _, total8, _ = oracle.oracle_ssim(a8, b8, taps=oracle.TAPS_RUNTIME)
+        assert abs(total8 / (w * h) - mean8) <= 1e-12

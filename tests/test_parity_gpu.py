@@ -62,7 +62,9 @@ def test_einstein(name, einstein, golden):
 
 
 @pytest.mark.parametrize("dims", [(1, 1), (2, 3), (7, 3), (5, 5), (11, 11), (16, 16), (255, 63), (256, 64), (257, 65), (300, 1),
-                                  (1, 300), (513, 129), (64, 75), (65, 11), (130, 200), (63, 8), (59, 6), (69, 20), (70, 9), (128, 3)])
+                                  (1, 300), (513, 129), (64, 75), (65, 11), (130, 200), (63, 8), (59, 6), (69, 20), (70, 9), (128, 3),
+                                  # width % 64 in 1..4: the right-edge patch of the second-to-last band reaches the end of its TMA box row
+                                  (65, 23), (66, 23), (67, 23), (68, 97), (132, 40), (1284, 31), (1283, 12)])
 def test_edge_dims(dims):
     w, h = dims
     a, b = synth_pair(w, h, 3)
@@ -80,6 +82,61 @@ def test_bbb_interleaved_crops(dims, bbb360):
     for ch in range(3):
         _check_pair("bbb360 %dx%d ch%d" % (w, h, ch), bbb360["jpg50"], bbb360["png"], width=w, height=h, step_a=3, step_b=3,
                     stride_a=640 * 3, stride_b=640 * 3, a_off=ch, b_off=ch)
+
+
+def test_bbb_full_frames_all_channels(bbb360_full, bbb1080_green, golden):
+    """The reference's bbb cases (tests/rmgr-ssim-tests.cpp:388-425) on the full frames: 640x360 PNG vs JPEG q50, every
+    channel of the interleaved RGB (step = 3), and the 1080p frame (green plane); against the vectors of the unmodified
+    double build recorded by make_golden.py and, when oracle/_ref is present, against that build run live."""
+    png, jpg = bbb360_full["png"], bbb360_full["jpg50"]
+    assert png.shape == (360, 640, 3)
+    for ch in range(3):
+        kw = dict(width=640, height=360, step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, a_off=ch, b_off=ch)
+        s, m = _check_pair("bbb360 full ch%d" % ch, jpg, png, **kw)
+        g = golden["bbb360_jpg50"]["640x360_ch%d" % ch]
+        assert abs(float(s) - g["ref_f64_auto"]) <= GLOBAL_TOL
+        assert abs(float(m.astype(np.float64).sum()) - g["ref_f64_auto_map_sum64"]) <= GLOBAL_TOL * 640 * 360
+        assert abs(float(m.min()) - g["ref_f64_auto_map_min"]) <= PIXEL_TOL
+        if oracle.have_ref():
+            r, rm = oracle.ref_ssim("f64", jpg, png, want_map=True, **kw)
+            assert abs(float(s) - float(r)) <= GLOBAL_TOL and np.abs(m - rm).max() <= PIXEL_TOL
+    # all three channels from one upload agree with the per-channel calls
+    sc, mc = api.compute_channels(jpg, png, want_map=True)
+    for ch in range(3):
+        assert abs(float(sc[ch]) - golden["bbb360_jpg50"]["640x360_ch%d" % ch]["ref_f64_auto"]) <= GLOBAL_TOL
+    png, jpg = bbb1080_green["png"], bbb1080_green["jpg50"]
+    s, m = _check_pair("bbb1080 green", jpg, png)
+    g = golden["bbb360_jpg50"]["1920x1080_green"]
+    assert abs(float(s) - g["ref_f64_auto"]) <= GLOBAL_TOL and abs(float(m.min()) - g["ref_f64_auto_map_min"]) <= PIXEL_TOL
+    if oracle.have_ref():
+        r, rm = oracle.ref_ssim("f64", jpg, png, want_map=True, openmp=True)
+        assert abs(float(s) - float(r)) <= GLOBAL_TOL and np.abs(m - rm).max() <= PIXEL_TOL
+
+
+def test_heap_allocator_and_deprecated_overload(einstein, golden):
+    """The remaining corners of the reference's test matrix (tests/rmgr-ssim-tests.cpp:468-507): Params with alloc/dealloc set
+    (the "heap" variant; scratch lives in device memory here, the callbacks are accepted and never called) and the
+    deprecated `float compute_ssim(const Params&)` overload, which returns the SSIM or -errno as a float (src/ssim.cpp:1108-1119)."""
+    from ssim_b200._abi import make_params
+    lib = api.rmgr_lib()
+    a, ref = einstein["blur"], einstein["einstein"]
+    want = float(golden["einstein"]["blur"]["golden_double_mean"])
+    m = np.zeros((256, 256), np.float32)
+    p = make_params(a, ref, 256, 256, ssim_map=m)
+    assert lib.rmgr_ssim_use_default_allocator(C.byref(p)) == 0 and p.alloc and p.dealloc
+    out = C.c_float()
+    assert lib.rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 0
+    assert abs(out.value - want) <= GLOBAL_TOL and abs(float(m.astype(np.float64).mean()) - want) <= GLOBAL_TOL
+    assert lib.rmgr_ssim_compute_ssim_openmp(C.byref(out), C.byref(p)) == 0 and abs(out.value - want) <= GLOBAL_TOL
+    dep = getattr(lib, "_ZN4rmgr4ssim12compute_ssimERKNS0_6ParamsE")             # float rmgr::ssim::compute_ssim(const Params&)
+    dep.restype = C.c_float
+    dep.argtypes = [C.c_void_p]
+    assert abs(dep(C.byref(p)) - want) <= GLOBAL_TOL
+    p2 = make_params(a, ref, 256, 0)
+    assert dep(C.byref(p2)) == -22.0                                              # -EINVAL as a float
+    p3 = make_params(a, ref, 256, 256)
+    p3.imgB.topLeft = None
+    assert dep(C.byref(p3)) == -22.0
 
 
 def test_synthetic_1080p_and_4k(golden):
