@@ -5,8 +5,8 @@
   python bench.py --impl reference ...                     (the reference's own FMA+OpenMP CPU path, oracle/_ref)
 
 A "step" is one pass of the hot path over one batch: FRAMES synthetic 4K frame pairs per GPU (SURVEY.md 8(d)
-recipe, seed 0x5517, resident in HBM before the timed region), one ssim_cuda_compute_device() call = one fused
-kernel launch + one tiny reduction launch, producing FRAMES maps and FRAMES global SSIM values.  Frames are
+recipe, seed 0x5517, resident in HBM before the timed region), one ssim_cuda_compute_device() call = ONE launch of
+the persistent fused kernel (per-frame reduction inside), producing FRAMES maps and FRAMES global SSIM values.  Frames are
 independent, so with N GPUs each rank owns its own FRAMES frames and there is no data-path collective (weak
 scaling); the timed region is bracketed by barrier + synchronize and the slowest rank's device time counts.
 
@@ -15,7 +15,7 @@ Printed JSON (one line, rank 0):
   e2e        same metric through the reference-facing API rmgr_ssim_compute_ssim() with pinned HOST buffers:
              H2D of both images and D2H of the map + scalar inside the timed region, one blocking call per frame,
              the calls issued from --e2e-threads host threads (default 2; the API is re-entrant like the reference's)
-  roofline   the fused kernel alone (CUDA events around K launches with no reduction kernel): algorithmic
+  roofline   the fused kernel (the only kernel of a step; CUDA events over the timed region): algorithmic
              230 flop/pixel / duration vs the FP32 FFMA peak 148 SM x 128 lanes x 2 x sm_max_mhz
              (MEASURED_PEAKS.json has no FP32 figure; tools/microbench measured 97-99% of this nominal peak),
              plus the HBM view (6 B/pixel with map vs the measured copy bandwidth)
@@ -63,6 +63,79 @@ def peaks():
             p = json.load(fh)
         return float(p["hbm_gbs"]), float(p["sm_max_mhz"]), "measured"
     return 6650.0, 1965.0, "fallback"          # B200_PROFILING.md fallback
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def pin_to_gpu_numa_node(index):
+    """Binds this process to the CPUs of the NUMA node the GPU hangs off (so that pinned staging memory, allocated afterwards,
+    is node-local).  Returns a short description for the bench line; silently does nothing where the topology is flat."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                  # nvml prints an 8-digit domain, sysfs a 4-digit one
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        if node < 0 or len(nodes) < 2:
+            return "flat topology (%d NUMA node(s)), no binding" % len(nodes)
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "bound to NUMA node %d (%d CPUs)" % (node, len(cpus))
+        return "NUMA node %d has no allowed CPUs, no binding" % node
+    except Exception as e:                                 # noqa: BLE001 -- topology files differ between hosts
+        return "no binding (%s)" % type(e).__name__
+
+
+def pcie_probe(torch, dist, world, dev, seconds=0.15):
+    """Concurrent H2D + D2H copy rates of THIS rank while every other rank does the same (barrier first): the PCIe / host
+    memory ceiling of the e2e leg at this N.  Returns (h2d GB/s, d2h GB/s) of this rank."""
+    n = 64 << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    both()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    reps = 0
+    t0 = time.perf_counter()
+    e[0].record(s1); e[2].record(s2)
+    while time.perf_counter() - t0 < seconds or reps < 4:
+        both()
+        reps += 1
+    e[1].record(s1); e[3].record(s2)
+    torch.cuda.synchronize()
+    return n * reps / e[0].elapsed_time(e[1]) / 1e6, n * reps / e[2].elapsed_time(e[3]) / 1e6
 
 
 def config(args, n):
@@ -148,7 +221,7 @@ def run_reference(args):
         line = {"impl": "reference", "metric": METRIC, "value": round(mpix, 2), "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(1e3 * sum(p[3] for p in per) / len(per), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config(args, n),
-                "cpu_baseline": {"value": round(mpix, 2), "unit": UNIT, "cores": per[0][1], "kind": "port",
+                "cpu_baseline": {"value": round(mpix, 2), "unit": UNIT, "cores": per[0][1], "cpu_model": cpu_model(), "kind": "port",
                                  "sample": "oracle/liboracle.so (plain-C double restatement, OpenMP) on 960x540 crops of the synthetic 4K pairs with map, 2 s per step"},
                 "e2e": {"value": round(mpix, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -157,12 +230,15 @@ def run_reference(args):
     frames = [synth_pair(W, H, f) for f in range(sample)]
     # untimed spin-up (thread pool, page faults, CPU clocks): a cold 0.2 s run measured 1.0 k Mpix/s where the warm
     # steady state of the same call is 1.8-1.9 k on the 16-core box; the reference deserves its steady state
-    time_reference(frames[:2], seconds=1.0)
+    time_reference(frames[:4], seconds=3.0)
     mpix, cores, done, dt, _ = time_reference(frames, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    cfg = config(args, n)
+    cfg["reference_arm_step"] = "a step of this arm is a bounded sample of the workload: %d of the %d pairs (ms_per_step is per sample step; value is a rate)" % (sample, args.frames)
+    cfg["sample_frames_per_step"] = sample
     line = {"impl": "reference", "metric": METRIC, "value": round(mpix, 2), "unit": UNIT, "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args, n),
-            "cpu_baseline": {"value": round(mpix, 2), "unit": UNIT, "cores": cores, "kind": "reference",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": round(mpix, 2), "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "reference",
                              "sample": "%d synthetic 4K pairs with map per step (frames 0..%d), %d steps, rmgr_ssim_compute_ssim_openmp of the unmodified float build" % (sample, sample - 1, args.steps)},
             "e2e": {"value": round(mpix, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -175,6 +251,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.period = 0.005
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -201,7 +278,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period)
 
     def summary(self):
         if not self.samples:
@@ -233,6 +310,20 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def one_call_us(fn, n=20):
+        """events around ONE call with an idle stream before it: the latency a caller sees, host-side launch cost included"""
+        ts = []
+        for i in range(n + 3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+        return statistics.median(ts), min(ts)
+
     # configs[1]: one 1920x1080 pair, global SSIM only (no map)
     w, h = 1920, 1080
     a = torch.empty((h, w), dtype=torch.uint8, device=dev)
@@ -240,9 +331,27 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
     sums = torch.empty(1, dtype=torch.float64, device=dev)
     val = torch.empty(1, dtype=torch.float32, device=dev)
     api.synth_fill(local, sh, a.data_ptr(), w, b.data_ptr(), w, w, h, 0, 0)
-    ms = timed(lambda: api.compute_device(local, sh, w, h, 0, h, 1, a.data_ptr(), w, 0, b.data_ptr(), w, 0, None, 0, 0, sums.data_ptr(), val.data_ptr()), 20)
-    out["1080p_pair_no_map"] = {"us_per_pair": round(ms * 1e3, 2), "mpix_per_s": round(w * h / ms / 1e3, 1), "ssim": float(val.item()),
-                                "note": "one pair per launch on every rank (latency view, L2-resident)"}
+    f1080 = lambda: api.compute_device(local, sh, w, h, 0, h, 1, a.data_ptr(), w, 0, b.data_ptr(), w, 0, None, 0, 0, sums.data_ptr(), val.data_ptr())  # noqa: E731
+    ms = timed(f1080, 50)
+    med, mn = one_call_us(f1080)
+    out["1080p_pair_no_map"] = {"us_per_pair": round(med, 2), "us_per_pair_min": round(mn, 2), "us_per_pair_queued": round(ms * 1e3, 2),
+                                "mpix_per_s": round(w * h / med, 1), "ssim": float(val.item()),
+                                "note": "one pair per call = one launch, on every rank: us_per_pair = events around a single call on an idle stream "
+                                        "(median of 20), us_per_pair_queued = 50 calls queued back to back (L2-resident inputs)"}
+    # the same config end to end: host buffers through rmgr_ssim_compute_ssim, no map (H2D of both images + the scalar back)
+    ha, hb = a.cpu().pin_memory(), b.cpu().pin_memory()
+    na, nb = ha.numpy(), hb.numpy()
+    for _ in range(3):
+        api.compute_ssim(na, nb)
+    barrier()
+    t0 = time.perf_counter()
+    reps = 30
+    for _ in range(reps):
+        e2e_val, _ = api.compute_ssim(na, nb)
+    dt = (time.perf_counter() - t0) / reps
+    out["1080p_pair_no_map"]["e2e_us_per_pair"] = round(dt * 1e6, 1)
+    out["1080p_pair_no_map"]["e2e_mpix_per_s"] = round(w * h / dt / 1e6, 1)
+    out["1080p_pair_no_map"]["e2e_ssim"] = float(e2e_val)
 
     # configs[3]: ONE 16384x16384 pair split into row strips with 5-row halos across the ranks, map strips written,
     # double partial sums all-reduced with NCCL inside the timed region
@@ -265,7 +374,7 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
                                           "ssim": float(parallel.mean_from_partials(float(sums.item()), W16, W16)),
                                           "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce of 1 double per step"}
     if world > 1:
-        # same strips, the cross-GPU sum fused into the reduction kernel: every rank's kernel stores its strip sum into every
+        # same strips, the cross-GPU sum fused into the kernel: the last warp of every rank's launch stores its strip sum into every
         # peer's exchange buffer over NVLink and adds up what lands in its own (ssim_cuda_compute_strip_allreduce); the
         # buffers of the other processes are mapped through CUDA IPC handles
         buf, handle = api.exchange_create(local)
@@ -286,9 +395,88 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
         torch.cuda.synchronize()
         out["16384x16384_strips_with_map_peer_memory"] = {"ms": round(ms2, 4), "mpix_per_s": round(W16 * W16 / ms2 / 1e3, 1), "scaling": "strong",
                                                           "ssim": float(allval.item()), "status": int(status.item()),
-                                                          "collective": "strip sums exchanged by NVLink peer stores inside the reduction kernel (no NCCL call)"}
+                                                          "collective": "strip sums exchanged by NVLink peer stores inside the fused kernel (one launch per rank, no NCCL call)"}
         dist.barrier()
+        del a, b, m
+        # strong-scaling efficiency needs the 1-GPU time of the same image on the same box: every rank times the whole image alone
+        a = torch.empty((W16, W16), dtype=torch.uint8, device=dev)
+        b = torch.empty((W16, W16), dtype=torch.uint8, device=dev)
+        m = torch.empty((W16, W16), dtype=torch.float32, device=dev)
+        api.synth_fill(local, sh, a.data_ptr(), W16, b.data_ptr(), W16, W16, W16, 0, 0)
+        ms1 = timed(lambda: api.compute_device(local, sh, W16, W16, 0, W16, 1, a.data_ptr(), W16, 0, b.data_ptr(), W16, 0, m.data_ptr(), W16, 0, sums.data_ptr(), None), 5)
+        for key, t in (("16384x16384_strips_with_map", ms), ("16384x16384_strips_with_map_peer_memory", ms2)):
+            out[key]["single_gpu_ms_same_box"] = round(ms1, 4)
+            out[key]["strong_scaling_efficiency"] = round(ms1 / (world * t), 4)
     del a, b, m
+
+    # SURVEY 8(e), single-process form: ssim_cuda_compute_strips() drives ALL visible GPUs of the box from rank 0 (host image in,
+    # strips + halos copied to every GPU, strip sums exchanged inside the kernels over peer memory), checked against the
+    # unmodified reference's value for the same synthetic image (tests/golden/golden.json)
+    ngpu = torch.cuda.device_count()
+    if rank == 0 and ngpu >= 1:
+        import numpy as np
+        a = torch.empty((W16, W16), dtype=torch.uint8, device=dev)
+        b = torch.empty((W16, W16), dtype=torch.uint8, device=dev)
+        api.synth_fill(local, sh, a.data_ptr(), W16, b.data_ptr(), W16, W16, W16, 0, 0)
+        ha, hb = a.cpu().pin_memory(), b.cpu().pin_memory()
+        del a, b
+        hm = torch.empty((W16, W16), dtype=torch.float32).pin_memory()
+        devices = list(range(min(ngpu, max(world, 1))))
+        with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as fh:
+            want = json.load(fh)["synthetic"]["16384x16384_f0"]["ref_f64_auto"]
+        import ctypes as C2
+        lib = api.cuda_lib()
+        got = C2.c_float()
+        devs = (C2.c_int * len(devices))(*devices)
+
+        def call():
+            rc = lib.ssim_cuda_compute_strips(len(devices), devs, W16, W16, ha.data_ptr(), 1, W16, hb.data_ptr(), 1, W16, hm.data_ptr(), 1, W16, C2.byref(got))
+            assert rc == 0, (rc, lib.ssim_cuda_last_error_string())
+
+        call()
+        t0 = time.perf_counter()
+        call()
+        dt = time.perf_counter() - t0
+        out["compute_strips_single_process"] = {"devices": devices, "ms_wall": round(dt * 1e3, 2), "mpix_per_s": round(W16 * W16 / dt / 1e6, 1),
+                                                "ssim": float(got.value), "reference_f64_ssim": want, "abs_diff": abs(float(got.value) - want),
+                                                "map_mean": float(hm.numpy().mean(dtype=np.float64)),
+                                                "note": "host image -> strips on all listed GPUs, maps back to the host; wall clock incl. all copies"}
+        assert abs(float(got.value) - want) <= 2e-6, out["compute_strips_single_process"]
+        del ha, hb, hm
+    barrier()
+
+    # all channels of an interleaved 1080p RGB pair (maps included) in one call vs one call per channel
+    if rank == 0:
+        import numpy as np
+        rng = np.random.default_rng(5)
+        ra = torch.from_numpy(rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)).pin_memory()
+        rb = torch.from_numpy(np.clip(ra.numpy().astype(np.int16) + rng.integers(-20, 21, ra.shape), 0, 255).astype(np.uint8)).pin_memory()
+        rm = torch.empty((1080, 1920, 3), dtype=torch.float32).pin_memory()
+        xa, xb, xm = ra.numpy(), rb.numpy(), rm.numpy()
+        lib = api.cuda_lib()
+        import ctypes as C2
+        outv = (C2.c_float * 3)()
+
+        def all_channels():
+            rc = lib.ssim_cuda_compute_channels(local, 1920, 1080, 3, xa.ctypes.data, 1920 * 3, xb.ctypes.data, 1920 * 3, xm.ctypes.data, 1920 * 3, outv)
+            assert rc == 0, rc
+
+        def per_channel():
+            for ch in range(3):
+                api.compute_ssim(xa, xb, width=1920, height=1080, step_a=3, step_b=3, stride_a=5760, stride_b=5760, a_off=ch, b_off=ch,
+                                 ssim_map=xm, map_step=3, map_stride=5760, map_off=ch)
+
+        res = {}
+        for name, fn in (("one_call_all_channels", all_channels), ("one_call_per_channel", per_channel)):
+            for _ in range(2):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                fn()
+            res[name + "_ms"] = round((time.perf_counter() - t0) / 10 * 1e3, 3)
+        res["ssim_rgb"] = [float(v) for v in outv]
+        out["1080p_rgb_pair_with_maps_host_api"] = res
+    barrier()
 
     # configs[4]: 4096 x 1080p pairs with maps, 512 per GPU (weak scaling; fewer per GPU when more than 8 ranks are not available)
     F = 512
@@ -343,6 +531,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == n, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (n, world)
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local)             # before any pinned allocation: staging memory lands on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = api.cuda_lib()
@@ -363,9 +552,9 @@ def run_ours(args):
         api.synth_fill(local, sh, dA[f].data_ptr(), W, dB[f].data_ptr(), W, W, H, 0, rank * F + f)
     torch.cuda.synchronize()
 
-    def step(with_reduce=True):
+    def step():
         api.compute_device(local, sh, W, H, 0, H, F, dA.data_ptr(), W, npx, dB.data_ptr(), W, npx, dMap.data_ptr(), W, npx,
-                           dSums.data_ptr() if with_reduce else None, dSsim.data_ptr() if with_reduce else None)
+                           dSums.data_ptr(), dSsim.data_ptr())
 
     def barrier():
         if world > 1:
@@ -394,15 +583,10 @@ def run_ours(args):
     value = n * F * npx * args.steps / (ms_max * 1e-3) / 1e6
     ssim_first = float(dSsim[0].item())
 
-    # ---- roofline: the fused kernel alone (no reduction launch), CUDA events on the launching stream
-    barrier()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(stream)
-    for _ in range(args.steps):
-        step(with_reduce=False)
-    k1.record(stream)
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
+    # ---- roofline: a step IS one launch of the fused kernel (nothing else runs in the timed region), so its average launch
+    # duration is this rank's timed region / steps
+    kernel_ms = ms / args.steps
+    sampler.period = 0.05                               # the device-timed region is over: sample lazily from here on
 
     # ---- one 4K pair per launch (latency view; BASELINE.md: <= 42.7 us is the 60% target)
     single = []
@@ -416,6 +600,17 @@ def run_ours(args):
         torch.cuda.synchronize()
         if i >= 3:
             single.append(s0.elapsed_time(s1) * 1e3)
+
+    torch.cuda.synchronize()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record(stream)
+    for i in range(40):
+        f = i % F
+        api.compute_device(local, sh, W, H, 0, H, 1, dA[f].data_ptr(), W, npx, dB[f].data_ptr(), W, npx, dMap[f].data_ptr(), W, npx,
+                           dSums.data_ptr(), dSsim.data_ptr())
+    q1.record(stream)
+    torch.cuda.synchronize()
+    single_queued_us = q0.elapsed_time(q1) * 1e3 / 40
 
     # ---- end to end through the reference-facing API with pinned host buffers (H2D + D2H inside the timed region)
     eF = min(F, 8)                                     # host frames kept pinned (rotated), 8 x 50 MB
@@ -452,6 +647,7 @@ def run_ours(args):
                 th.join()
         return last[(F - 1) % e2e_threads]
 
+    h2d_gbs, d2h_gbs = pcie_probe(torch, dist, world, dev)
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(1):
         e2e_step()
@@ -466,6 +662,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(td, op=dist.ReduceOp.MAX)
     e2e_value = n * F * npx * e2e_steps / float(td.item()) / 1e6
+    # this rank's full-duplex PCIe bound for the metric (2 B/pixel in, 4 B/pixel out, both directions busy at once), summed over ranks
+    pb = torch.tensor([1.0 / max(2.0 / (h2d_gbs * 1e3), 4.0 / (d2h_gbs * 1e3)), h2d_gbs, d2h_gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pb, op=dist.ReduceOp.SUM)
+    pcie_bound_mpix, h2d_all, d2h_all = (float(v) for v in pb.tolist())
 
     extras = None if args.no_extras else run_extras(args, api, torch, dist, local, rank, world, stream, barrier)
 
@@ -481,13 +682,17 @@ def run_ours(args):
     fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # TFLOP/s
     achieved = FLOP_PER_PIXEL * F * npx / (kernel_ms * 1e-3) / 1e12
     hbm_achieved = BYTES_PER_PIXEL_MAP * F * npx / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes of one launch cannot be measured outside a profiler: quoted from the committed ncu capture of this kernel,
+    # with its provenance (scaled by the frame count: the capture's traffic is proportional to it)
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "fused_kernel_dram_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        if tj.get("frames") == F:
-            traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("frames") and tj.get("dram_bytes_per_launch"):
+            traffic = round(tj["dram_bytes_per_launch"] * F / tj["frames"])
+            traffic_source = "ncu --set full capture %s (%s, %d frames per launch, kernel %s), scaled to %d frames" % (
+                tj.get("capture", "?"), tj.get("captured_at_commit", "?"), tj["frames"], tj.get("kernel", "?"), F)
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -495,16 +700,26 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": F * 2 * npx, "d2h_bytes_per_step": F * (npx * 4 + 4),
                     "api": "rmgr_ssim_compute_ssim (librmgr-ssim.so), one blocking call per 4K pair, pinned host buffers, calls issued from %d host thread(s)" % e2e_threads,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps,
+                    "pcie_bound_mpix": round(pcie_bound_mpix, 1), "frac_of_pcie_bound": round(e2e_value / pcie_bound_mpix, 4),
+                    "pcie_probe": {"h2d_gbs_all_ranks": round(h2d_all, 1), "d2h_gbs_all_ranks": round(d2h_all, 1),
+                                   "how": "every rank copies 64 MiB pinned buffers H2D and D2H at the same time on two streams, all ranks concurrently; "
+                                          "bound = sum over ranks of 1 / max(2 B/px / h2d, 4 B/px / d2h)"},
+                    "host_binding": numa},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": round(achieved, 2), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
-                         "frac": round(achieved / fp32_peak, 4), "traffic": traffic,
-                         "kernel": "ssim_fused_kernel<true>", "kernel_ms_per_launch": round(kernel_ms, 4),
+                         "frac": round(achieved / fp32_peak, 4), "traffic": traffic, "traffic_source": traffic_source,
+                         "algorithmic_bytes": int(BYTES_PER_PIXEL_MAP * F * npx),
+                         "kernel": "void ssimk::ssim_fused_kernel<true, false>(CUtensorMap_st, CUtensorMap_st, ssimk::FusedParams, ssimk::ExchangeParams)",
+                         "kernel_ms_per_launch": round(kernel_ms, 4),
                          "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (%s MEASURED_PEAKS.json sm_max_mhz); FFMA microbench reaches 97-99%% of it" % peak_kind,
                          "hbm": {"achieved": round(hbm_achieved, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(hbm_achieved / hbm_gbs, 4),
                                  "peak_source": "%s copy bandwidth" % peak_kind}},
             "single_pair_us": {"median": round(statistics.median(single), 2), "min": round(min(single), 2),
-                               "mpix_per_s_at_median": round(npx / statistics.median(single), 1)},
+                               "mpix_per_s_at_median": round(npx / statistics.median(single), 1),
+                               "queued_us_per_pair": round(single_queued_us, 2),
+                               "note": "one 4K pair with map per call = one launch: median/min = events around a single call on an idle stream "
+                                       "(host-side launch cost included), queued = 40 calls (rotating frames) queued back to back"},
             "ssim_frame0": ssim_first, "ssim_e2e_last": float(e2e_last)}
     if extras is not None:
         line["other_configs"] = extras
@@ -514,12 +729,12 @@ def run_ours(args):
         if oracle.have_ref():
             frames = [(nA[k], nB[k]) for k in range(min(eF, 4))]
             mpix, cores, done, cdt, cpu_ssim = time_reference(frames, seconds=args.cpu_seconds)
-            line["cpu_baseline"] = {"value": round(mpix, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+            line["cpu_baseline"] = {"value": round(mpix, 1), "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "reference",
                                     "sample": "%d calls of rmgr_ssim_compute_ssim_openmp (unmodified float build, AUTO=FMA dispatch) on synthetic 4K pairs with map, %.1f s" % (done, cdt),
                                     "ssim_last": cpu_ssim}
         else:
             mpix, cores, done, cdt, cpu_ssim = time_port(min(args.cpu_seconds, 10.0))
-            line["cpu_baseline"] = {"value": round(mpix, 2), "unit": UNIT, "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": round(mpix, 2), "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port",
                                     "sample": "%d calls of oracle/liboracle.so (plain-C double restatement, OpenMP) on 960x540 crops of the synthetic 4K pairs with map, %.1f s" % (done, cdt),
                                     "ssim_last": cpu_ssim}
     print(json.dumps(line))

@@ -177,6 +177,13 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
  */
 void ssim_cuda_set_tuning(int maxCtasPerSm, int minSlotRows);
 
+/*
+ * Development aid: while dTimes (device memory, 32 x 64-bit words per warp pair of the persistent grid, i.e. at least
+ * 32 * 8 * numSMs words) is non-NULL, every launch records the %globaltimer at which each consumer warp started [0], finished
+ * its share [1] and finished its k-th 8-row ring unit [1+k]; NULL switches it off.  Used by tools/dev/slot_times.py to look at load balance.
+ */
+void ssim_cuda_debug_slot_times(unsigned long long* dTimes);
+
 #ifdef __cplusplus
 }
 #endif

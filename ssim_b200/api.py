@@ -80,6 +80,8 @@ def cuda_lib():
     lib.ssim_cuda_synth_fill.restype = C.c_int
     lib.ssim_cuda_set_tuning.argtypes = [C.c_int, C.c_int]
     lib.ssim_cuda_set_tuning.restype = None
+    lib.ssim_cuda_debug_slot_times.argtypes = [C.c_void_p]
+    lib.ssim_cuda_debug_slot_times.restype = None
     lib._bound = True
     return lib
 

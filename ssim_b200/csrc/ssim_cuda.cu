@@ -39,6 +39,7 @@ thread_local char g_err[512] = "";
 thread_local int  g_lastLaunches = 0;
 std::atomic<int> g_minSlotRows{0};       // tuning knobs (0 = automatic), see ssim_cuda_set_tuning()
 std::atomic<int> g_maxCtasPerSm{0};
+std::atomic<unsigned long long*> g_dbgTimes{nullptr};   // development aid, see ssim_cuda_debug_slot_times()
 
 int fail(int code, const char* fmt, ...)
 {
@@ -411,7 +412,7 @@ int get_workspace(Context* c, cudaStream_t stream, size_t frames, size_t cells, 
 int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_t srcRows, uint32_t outY0, uint32_t outRows,
                         uint32_t frames, const uint8_t* dA, size_t pitchA, size_t frameStrideA, const uint8_t* dB, size_t pitchB,
                         size_t frameStrideB, float* dMap, size_t mapPitch, size_t mapFrameStride, double* dSums, float* dSsim,
-                        int elemBytes = 1, const ssimk::ExchangeParams* xchg = nullptr)
+                        int elemBytes = 1, const ssimk::ExchangeParams* xchg = nullptr, size_t mapStep = 1)
 {
     g_lastLaunches = 0;
     if (width == 0 || srcRows == 0 || outRows == 0 || frames == 0) return fail(EINVAL, "width, rows and frames must be non-zero");
@@ -422,7 +423,8 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (((uintptr_t)dA | (uintptr_t)dB | pitchA | pitchB) & 15) return fail(EINVAL, "plane base addresses and pitches must be multiples of 16 bytes");
     if (frames > 1 && ((frameStrideA | frameStrideB) & 15)) return fail(EINVAL, "frame strides must be multiples of 16 bytes");
     if (pitchA < (size_t)width * elemBytes || pitchB < (size_t)width * elemBytes) return fail(EINVAL, "pitch smaller than width");
-    if (dMap && mapPitch < width) return fail(EINVAL, "map pitch smaller than width");
+    if (dMap && (mapStep < 1 || mapPitch < (size_t)width * mapStep)) return fail(EINVAL, "map pitch smaller than width");
+    if (dMap && mapStep != 1 && elemBytes != 1) return fail(EINVAL, "maps with a pixel step are supported for 8-bit images only");
 
     ssimk::SlotPlan plan;
     if (!plan_for(c, width, outRows, frames, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
@@ -440,7 +442,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.a = dA; p.b = dB;
     p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
     p.pitchB = (long long)pitchB; p.frameStrideB = (long long)frameStrideB;
-    p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride;
+    p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride; p.mapStep = (long long)mapStep;
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.geo = ssimk::make_slot_geo(plan, width);
     p.partials = ws.partials; p.frameDone = ws.frameDone; p.entries = plan.entries;
@@ -453,6 +455,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
         p.backoffNs = backoff;
     }
     p.eps2 = c->eps2;
+    p.dbgTimes = g_dbgTimes.load(std::memory_order_relaxed);
     CU_TRY(ssimk::launch_fused(stream, *tmA, *tmB, p, xchg));      // the ONLY launch: reduction (and exchange) happen inside
     g_lastLaunches = 1;
     return 0;
@@ -551,13 +554,14 @@ int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, ui
 
     // map destination: write straight into a canonical device map of the caller, else into scratch
     float* dMap = nullptr;
-    size_t dMapPitch = 0;
+    size_t dMapPitch = 0, dMapStep = 1;
     bool mapDirect = false;
     Where mapWhere = Where::Host;
     if (map) {
         mapWhere = classify(map);
-        if (mapWhere == Where::Device && mapStep == 1 && mapStride >= (ptrdiff_t)W) {
-            dMap = map; dMapPitch = (size_t)mapStride; mapDirect = true;
+        if (mapWhere == Where::Device && mapStep >= 1 && mapStride >= (ptrdiff_t)W * mapStep && (mapStep == 1 || elemBytes == 1)) {
+            // the kernel writes the caller's device map in place, interleaved neighbours (step > 1) stay untouched
+            dMap = map; dMapPitch = (size_t)mapStride; dMapStep = (size_t)mapStep; mapDirect = true;
         } else {
             dMapPitch = align_up(W, 4);
             if ((rc = c->map.ensure(dMapPitch * outRows * sizeof(float)))) return rc;
@@ -569,7 +573,7 @@ int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, ui
     float* dSsim = (float*)((char*)c->scalars.ptr + 8);
 
     rc = compute_device_impl(c, s, W, srcRows, outY0, outRows, 1, pa, pitchA, 0, pb, pitchB, 0, dMap, dMapPitch, 0, dSum,
-                             wantSsim ? dSsim : nullptr, elemBytes, xchg);
+                             wantSsim ? dSsim : nullptr, elemBytes, xchg, dMapStep);
     if (rc) return rc;
 
     job->c = c; job->W = W; job->outRows = outRows; job->map = map; job->mapStep = mapStep; job->mapStride = mapStride;
@@ -1048,18 +1052,16 @@ int compute_channels_body(Context* c, uint32_t width, uint32_t height, uint32_t 
     DEVICE_GUARD(c->device);
     cudaStream_t s = c->stream;
     const size_t rawPitch = align_up(rowBytes, 16), pitch = align_up(width, 16), plane = pitch * height;
-    const size_t mapPitch = align_up(width, 4), mapPlane = mapPitch * height;
     if ((rc = c->rawA.ensure(rawPitch * height)) || (rc = c->rawB.ensure(rawPitch * height))) return rc;
     if ((rc = c->planeA.ensure(plane * channels)) || (rc = c->planeB.ensure(plane * channels))) return rc;
     if ((rc = c->scalars.ensure((sizeof(double) + sizeof(float)) * 16))) return rc;
-    float* dMaps = nullptr;
     float* dInter = nullptr;
     if (map) {
-        if ((rc = c->map.ensure((mapPlane * channels + rowBytes * height) * sizeof(float)))) return rc;
-        dMaps = (float*)c->map.ptr;
-        dInter = dMaps + mapPlane * channels;
+        if ((rc = c->map.ensure(rowBytes * height * sizeof(float)))) return rc;
+        dInter = (float*)c->map.ptr;
     }
-    // one upload of the interleaved bytes, one split into planes, ONE fused launch with the channels as frames
+    // one upload of the interleaved bytes, one split into planes, ONE fused launch with the channels as frames that writes the
+    // interleaved map directly (pixel step = channels, "frame" stride = 1 float)
     CU_TRY(cudaMemcpy2DAsync(c->rawA.ptr, rawPitch, a, (size_t)strideA, rowBytes, height, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpy2DAsync(c->rawB.ptr, rawPitch, b, (size_t)strideB, rowBytes, height, cudaMemcpyHostToDevice, s));
     CU_TRY(ssimk::launch_deinterleave_u8(s, (uint8_t*)c->planeA.ptr, (long long)pitch, (long long)plane, (const uint8_t*)c->rawA.ptr, (long long)rawPitch, (int)channels, (int)width, (int)height));
@@ -1067,12 +1069,11 @@ int compute_channels_body(Context* c, uint32_t width, uint32_t height, uint32_t 
     double* dSums = (double*)c->scalars.ptr;
     float* dSsim = (float*)((char*)c->scalars.ptr + sizeof(double) * 16);
     rc = compute_device_impl(c, s, width, height, 0, height, channels, (const uint8_t*)c->planeA.ptr, pitch, plane, (const uint8_t*)c->planeB.ptr, pitch, plane,
-                             dMaps, mapPitch, mapPlane, dSums, dSsim);
+                             dInter, rowBytes, 1, dSums, dSsim, 1, nullptr, channels);
     if (rc) return rc;
     float hostSsim[16];
     if (ssim) CU_TRY(cudaMemcpyAsync(hostSsim, dSsim, sizeof(float) * channels, cudaMemcpyDeviceToHost, s));
     if (map) {
-        CU_TRY(ssimk::launch_interleave_map(s, dInter, (long long)rowBytes, dMaps, (long long)mapPitch, (long long)mapPlane, (int)channels, (int)width, (int)height));
         CU_TRY(cudaMemcpy2DAsync(map, (size_t)mapStride * sizeof(float), dInter, rowBytes * sizeof(float), rowBytes * sizeof(float), height, cudaMemcpyDeviceToHost, s));
     }
     CU_TRY(cudaStreamSynchronize(s));
@@ -1216,6 +1217,8 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
     CU_TRY(ssimk::launch_synth_fill((cudaStream_t)stream, dA, (long long)pitchA, dB, (long long)pitchB, (int)width, (int)rows, (int)y0, frame, seed));
     return 0;
 }
+
+void ssim_cuda_debug_slot_times(unsigned long long* dTimes) { g_dbgTimes.store(dTimes, std::memory_order_relaxed); }
 
 void ssim_cuda_set_tuning(int maxCtasPerSm, int minSlotRows)
 {

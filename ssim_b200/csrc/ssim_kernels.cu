@@ -45,7 +45,8 @@ __device__ __forceinline__ u64 lds64(uint32_t addr) {
     u64 v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr)); return v;
 }
 __device__ __forceinline__ void sts64(uint32_t addr, u64 v) {
-    asm volatile("st.shared.u64 [%0], %1;" :: "r"(addr), "l"(v) : "memory");
+    float lo, hi; unpack2(v, lo, hi);
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(lo), "f"(hi) : "memory");
 }
 
 template <int kOff>
@@ -53,10 +54,15 @@ __device__ __forceinline__ void stg_f32(unsigned long long addr, float v) {
     asm volatile("st.global.f32 [%0+%1], %2;" :: "l"(addr), "n"(kOff), "f"(v) : "memory");
 }
 
-// predicated store: the predicate travels as a register, the store stays a single predicated STG (no branch)
-template <int kOff>
-__device__ __forceinline__ void stg_f32_if(unsigned long long addr, float v, uint32_t pred) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q st.global.f32 [%0+%1], %2;\n}\n" :: "l"(addr), "n"(kOff), "f"(v), "r"(pred) : "memory");
+// "if (pred) { store v; sum += v; }" as ONE predicate and two predicated instructions (no branch): the predicate travels as a
+// register between rows; kStore = false leaves only the predicated add
+template <int kOff, bool kStore>
+__device__ __forceinline__ void store_and_sum_if(unsigned long long addr, float v, uint32_t pred, float& sum) {
+    if (kStore)
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %4, 0;\n@q st.global.f32 [%1+%2], %3;\n@q add.f32 %0, %0, %3;\n}\n"
+                     : "+f"(sum) : "l"(addr), "n"(kOff), "f"(v), "r"(pred) : "memory");
+    else
+        asm("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q add.f32 %0, %0, %1;\n}\n" : "+f"(sum) : "f"(v), "r"(pred));
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -174,47 +180,46 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     // clamp(y + hr) of it.  Columns outside the plane arrive as zeros and are patched after landing (src/ssim.cpp:541-554).
     const int lastBoxY = max(p.srcRows - kLoadRows, 0);
 
-    // The ISSUE cursor runs exactly kStages blocks ahead of the compute cursor, across piece boundaries; it enters a piece
-    // only when it is about to load that piece's first block, so that while the compute cursor enters piece k the issue
-    // cursor is still inside piece k (every piece has >= 2 blocks) and its centring pixels are the ones to use.
-    PieceCursor curI;
-    cursor_init(curI, p.geo, slot);
-    PieceGeo gI;
-    gI.nBlk = 0; gI.frame = gI.bx = gI.inY0 = 0;
-    int blkI = 0;
-    bool haveI = false;
-    uint32_t issued = 0;                                    // blocks requested so far; block n uses stage n & 1
-    float caI = 0.f, cbI = 0.f;
-    auto issue_next = [&](bool patched) {
-        if (blkI == gI.nBlk) {
-            Piece pc;
-            haveI = cursor_next(curI, p.geo, pc);
-            if (haveI) { piece_geo(p, pc, gI); piece_centre<kU16>(p, gI, caI, cbI); blkI = 0; }
-        }
-        if (haveI) {
-            const uint32_t stage = issued & 1u;
-            if (lane == 0) {
-                // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes).
-                // The stage may be refilled once EVERY lane's loads of its previous contents have been performed: each lane
-                // releases the stage through an mbarrier (count 32) and lane 0 acquires it before re-arming the TMA barrier.
-                // Program order plus __syncwarp() is not enough here -- with the refill issued straight after the loads,
-                // tools/dev/stress.py saw rare 8-row x 16-column blocks computed from the NEXT box's bytes.
-                if (issued >= (uint32_t)kStages) {
-                    while (!mbar_test(barStageEmpty + 8 * stage, ((issued >> 1) - 1u) & 1u)) { }
-                    if (patched) fence_proxy_async();       // the patch stores (generic proxy) precede the TMA write
-                }
-                const uint32_t bar = barTma + 8 * stage;
-                const uint32_t dst = pairSmem + stage * kStageBytes;
-                const int y0 = min(max(gI.inY0 + blkI * kLoadRows, 0), lastBoxY);
-                mbar_arrive_expect_tx(bar, kStageBytes);
-                tma_load_3d(dst, tmA, gI.bx - G::kBoxLeftElems, y0, gI.frame, bar);
-                tma_load_3d(dst + kImgStageBytes, tmB, gI.bx - G::kBoxLeftElems, y0, gI.frame, bar);
+    // TMA issue runs exactly kStages (= 2) blocks ahead of the computation, across piece boundaries: the block that refills
+    // the stage of block `blk` of the current piece is block blk + 2 of the same piece or, in its last two blocks, block 0
+    // or 1 of the NEXT piece (every piece has >= 2 blocks), whose geometry and centring pixels are fetched one piece ahead.
+    auto issue = [&](const PieceGeo& ge, int blkIdx, uint32_t stage, bool refill, uint32_t emptyParity, bool patched) {
+        if (lane == 0) {
+            // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes).
+            // The stage may be refilled once EVERY lane's loads of its previous contents have been performed: each lane
+            // releases the stage through an mbarrier (count 32) and lane 0 acquires it before re-arming the TMA barrier.
+            // Program order plus __syncwarp() is not enough here -- with the refill issued straight after the loads,
+            // tools/dev/stress.py saw rare 8-row x 16-column blocks computed from the NEXT box's bytes.
+            if (refill) {
+                while (!mbar_test(barStageEmpty + 8 * stage, emptyParity)) { }
+                if (patched) fence_proxy_async();           // the patch stores (generic proxy) precede the TMA write
             }
-            ++blkI; ++issued;
+            const uint32_t bar = barTma + 8 * stage;
+            const uint32_t dst = pairSmem + stage * kStageBytes;
+            const int y0 = min(max(ge.inY0 + blkIdx * kLoadRows, 0), lastBoxY);
+            mbar_arrive_expect_tx(bar, kStageBytes);
+            tma_load_3d(dst, tmA, ge.bx - G::kBoxLeftElems, y0, ge.frame, bar);
+            tma_load_3d(dst + kImgStageBytes, tmB, ge.bx - G::kBoxLeftElems, y0, ge.frame, bar);
         }
     };
-    #pragma unroll
-    for (int s = 0; s < kStages; ++s) issue_next(false);
+    PieceCursor cur;
+    cursor_init(cur, p.geo, slot);
+    PieceGeo g, gN;
+    float ca, cb, caN = 0.f, cbN = 0.f;
+    {
+        Piece pc;
+        if (!cursor_next(cur, p.geo, pc)) return;           // a slot without any output row
+        piece_geo(p, pc, g);
+        piece_centre<kU16>(p, g, ca, cb);
+    }
+    issue(g, 0, 0, false, 0, false);
+    issue(g, 1, 1, false, 0, false);
+    bool haveN;
+    {
+        Piece pc;
+        haveN = cursor_next(cur, p.geo, pc);
+        if (haveN) { piece_geo(p, pc, gN); piece_centre<kU16>(p, gN, caN, cbN); } else gN = g;
+    }
 
     const uint32_t magic = p.magic;                    // 0x4B000000, passed as a parameter so that it lives in a register and
                                                        // PRMT takes the byte selector as its immediate (no per-PRMT selector MOV)
@@ -242,16 +247,10 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     #pragma unroll
     for (int m = 0; m < 4; ++m) laneDst[m] = ringBase + hr * kRingRowBytes + hq * 128 + ((uint32_t)(m ^ hq) << 3);
 
-    PieceCursor curC;
-    cursor_init(curC, p.geo, slot);
     uint32_t gblk = 0;                                      // blocks computed so far
     uint32_t unit = 0, lapParity = 0;                       // ring unit block gblk goes to, parity of the ring lap it belongs to
-    Piece pc;
     #pragma unroll 1
-    while (cursor_next(curC, p.geo, pc)) {
-        PieceGeo g;
-        piece_geo(p, pc, g);
-        const float ca = caI, cb = cbI;                      // see the issue cursor
+    for (;;) {
         // (a - ca, b - cb) from the bytes: PRMT builds 2^23 + byte, one packed FADD removes 2^23 + centre (exact)
         const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));
         const float k2 = -0.5f * p.eps2 * (ca - cb) * (ca - cb);  // see the formula in consumer_warp()
@@ -351,7 +350,9 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
                     else if (k > 0 && k <= 10) { hab[j] = fma2(ab, TAP(k), hab[j]); hsp[j] = fma2(sp, TAP(k), hsp[j]); }
                 }
                 if (ii == 10) {
-                    issue_next(patched);                                // refill this block's stage (two blocks ahead)
+                    // refill this block's stage with the block two ahead (all lanes have released it above)
+                    if (blk + kStages < g.nBlk) issue(g, blk + kStages, stage, true, (gblk >> 1) & 1u, patched);
+                    else if (haveN)             issue(gN, blk + kStages - g.nBlk, stage, true, (gblk >> 1) & 1u, patched);
                     // first store of the block: the ring unit must have been drained by the consumer (waiting here, not at the
                     // top, lets the loads and the first 10 columns of math overlap the wait); parity of the previous lap --
                     // the first lap passes at once on the fresh barrier
@@ -369,6 +370,11 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             ++gblk;
             if (++unit == (uint32_t)G::kRingUnits) { unit = 0; lapParity ^= 1u; }
         }
+        if (!haveN) break;
+        g = gN; ca = caN; cb = cbN;
+        Piece pc;
+        haveN = cursor_next(cur, p.geo, pc);
+        if (haveN) { piece_geo(p, pc, gN); piece_centre<kU16>(p, gN, caN, cbN); }
     }
     #undef TAP
 }
@@ -384,36 +390,44 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-__device__ __forceinline__ uint32_t slot_of_unit(const SlotGeo& g, uint32_t q)
+__device__ __forceinline__ uint32_t share_of_unit(const SlotGeo& g, uint32_t q)
 {
     const uint32_t big = g.shareR * (g.shareQ + 1u);
     return q < big ? q / (g.shareQ + 1u) : g.shareR + (q - big) / g.shareQ;
 }
-__device__ __forceinline__ uint32_t first_unit_of_slot(const SlotGeo& g, uint32_t s) { return s * g.shareQ + (s < g.shareR ? s : g.shareR); }
 
 // Slot `slot` has written its entry for frame f (entry index = f - first frame its unit range touches; slots that hold
 // none of the frame's rows deliver 0) and now arrives at the frame's counter: threadFenceReduction pattern.
 __device__ __forceinline__ void frame_arrive(const FusedParams& p, const ExchangeParams& x, int f, int lane)
 {
     const uint32_t frameUnits = p.geo.bands * p.geo.colUnits;
-    const uint32_t sLo = slot_of_unit(p.geo, (uint32_t)f * frameUnits);
-    const uint32_t sHi = slot_of_unit(p.geo, (uint32_t)(f + 1) * frameUnits - 1u);
+    const uint32_t u0 = (uint32_t)f * frameUnits, u1 = u0 + frameUnits;
+    // the slots that deliver to this frame are those whose units intersect the frame's: a contiguous run [sLo, sHi]
+    const uint32_t sLo = share_of_unit(p.geo, u0), sHi = share_of_unit(p.geo, u1 - 1u);
     __threadfence();
     unsigned prev = 0;
     if (lane == 0) prev = atomicAdd(p.frameDone + f, 1u);
     prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev != sHi - sLo) return;                      // not the last of the sHi - sLo + 1 slots that own units of this frame
+    if (prev != sHi - sLo) return;                      // not the last of the sHi - sLo + 1 slots
     __threadfence();
+    // fixed order (slot order, lanes strided, then the shuffle tree): deterministic.  The loads are issued in batches so
+    // that their L2 latencies overlap (one dependent load per add cost 13 us for the 1184 partials of a single frame).
     double acc = 0.0;
-    if (p.frames == 1) {
-        #pragma unroll 8
-        for (uint32_t s = sLo + lane; s <= sHi; s += 32) acc += __ldcg(p.partials + s);          // entries == 1
-    } else {
-        #pragma unroll 4
-        for (uint32_t s = sLo + lane; s <= sHi; s += 32) {
-            const uint32_t fFirst = first_unit_of_slot(p.geo, s) / frameUnits;                   // first frame slot s touches
-            acc += __ldcg(p.partials + (size_t)s * p.entries + ((uint32_t)f - fFirst));
+    constexpr int kBatch = 8;
+    for (uint32_t s0 = sLo + lane; s0 <= sHi; s0 += 32 * kBatch) {
+        double v[kBatch];
+        #pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const uint32_t s = s0 + 32u * k;
+            v[k] = 0.0;
+            if (s <= sHi) {
+                uint32_t e = 0;                                                             // a single frame: entries == 1
+                if (p.frames != 1) { uint32_t q0, q1; slot_units(p.geo, s, q0, q1); e = (uint32_t)f - q0 / frameUnits; }
+                v[k] = __ldcg(p.partials + (size_t)s * p.entries + e);
+            }
         }
+        #pragma unroll
+        for (int k = 0; k < kBatch; ++k) acc += v[k];
     }
     acc = warp_sum(acc);
     if (lane == 0) {
@@ -513,7 +527,9 @@ __device__ __forceinline__ void vertical_row(const int T, u64 (&qab0)[kTaps], u6
     sv0 = sv[0]; sv1 = sv[1];
 }
 
-template <bool kMap, bool kU16>
+// kMap: 0 = no map, 1 = dense map rows (x step 1), 2 = map with a pixel step (interleaved maps: all channels of an image
+// are written by one launch straight into the caller's layout, map[(y*pitch) + x*step + channel])
+template <int kMap, bool kU16>
 __device__ __forceinline__ void consumer_warp(const FusedParams& p, const ExchangeParams& x, uint32_t slot, int lane, uint32_t pairSmem, uint32_t barBase)
 {
     typedef PixGeo<kU16> G;
@@ -530,13 +546,14 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
 
     // Eleven in-place accumulators per plane pair and column: slot s accumulates the output row whose first input row
     // is == s (mod 11).  At row t of a body slot s receives tap (t - s) mod 11; the slot receiving tap 0 is re-initialised,
-    // the slot receiving tap 10 is complete.  All indices are compile-time constants.  A new piece simply starts a new body:
-    // whatever the slots still hold only reaches outputs of the first 10 rows, which are never stored.
+    // the slot receiving tap 10 is complete.  All indices are compile-time constants.  They are cleared at the start of every
+    // piece: not needed for the results (what they hold only reaches the 10 warm-up rows, which are never stored), but it
+    // ends their live ranges at the piece boundary, so the per-frame delivery code between two pieces gets registers without
+    // spilling 88 accumulator registers around it.
     u64 qab0[kTaps], qsp0[kTaps], qab1[kTaps], qsp1[kTaps];
-    #pragma unroll
-    for (int m = 0; m < kTaps; ++m) qab0[m] = qsp0[m] = qab1[m] = qsp1[m] = 0ull;
 
     const unsigned long long mapPitchBytes = (unsigned long long)p.mapPitch * sizeof(float);
+    const unsigned long long mapCol1Bytes = (unsigned long long)p.mapStep * 32 * sizeof(float);      // kMap == 2: this lane's second column
     // ring position (warp-uniform): the unit being read, the parity of the ring lap it belongs to, and this lane's two
     // shared-memory addresses of the next row (they advance by one ring row per input row; wrapping happens at unit ends)
     uint32_t unit = 0, lap = 0;
@@ -544,12 +561,16 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
 
     // partial sums: one entry per frame this slot's unit range touches, entry index = frame - first such frame
     const uint32_t frameUnits = p.geo.bands * p.geo.colUnits;
-    const uint32_t q0 = first_unit_of_slot(p.geo, slot), qEnd = q0 + p.geo.shareQ + (slot < p.geo.shareR ? 1u : 0u);
+    uint32_t q0, qEnd;
+    slot_units(p.geo, slot, q0, qEnd);
+    if (q0 >= qEnd) return;                                 // an empty share (weighted split of a very short range): nothing to deliver
     const int fFirst = (int)(q0 / frameUnits), fLast = (int)((qEnd - 1u) / frameUnits);
     double* myPart = p.partials + (size_t)slot * p.entries;
     int curFrame = fFirst;                                  // frames below this one have been delivered
     double total = 0.0;                                     // this lane's sum of curFrame's values so far
 
+    uint32_t dbgUnits = 0;
+    if (p.dbgTimes && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbgTimes[kDbgWords * slot] = t; }
     PieceCursor cur;
     cursor_init(cur, p.geo, slot);
     #pragma unroll 1
@@ -569,9 +590,14 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
             }
             total = 0.0;
         }
-        if (!have) break;
+        if (!have) {
+            if (p.dbgTimes && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbgTimes[kDbgWords * slot + 1] = t; }
+            break;
+        }
         PieceGeo g;
         piece_geo(p, pc, g);
+        #pragma unroll
+        for (int m = 0; m < kTaps; ++m) qab0[m] = qsp0[m] = qab1[m] = qsp1[m] = 0ull;
         float ca, cb;
         piece_centre<kU16>(p, g, ca, cb);
         const bool colOk0 = g.bx + lane < p.width;
@@ -580,7 +606,8 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
         // piece, never dereferenced there); the second column is an immediate offset.  Stores are written in PTX so
         // that the address arithmetic stays these two adds per row.
         unsigned long long mapAddr = 0;
-        if (kMap) mapAddr = (unsigned long long)(p.map + (long long)g.frame * p.mapFrameStride + (long long)(pc.r0 - 2 * kHalo) * p.mapPitch + g.bx + lane);
+        if (kMap == 1) mapAddr = (unsigned long long)(p.map + (long long)g.frame * p.mapFrameStride + (long long)(pc.r0 - 2 * kHalo) * p.mapPitch + g.bx + lane);
+        if (kMap == 2) mapAddr = (unsigned long long)(p.map + (long long)g.frame * p.mapFrameStride + (long long)(pc.r0 - 2 * kHalo) * p.mapPitch + (long long)(g.bx + lane) * p.mapStep);
 
         // Per-row bookkeeping is ONE countdown: n = rows until the next event, the events being the end of the ring unit
         // (release it, acquire the next one), the end of the 10 warm-up rows (outputs become valid) and the end of the
@@ -589,41 +616,66 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
         int step = min(unitLeft, min(warmLeft, pieceLeft)), n = step;
         uint32_t pred0 = 0, pred1 = 0;                                   // "store and sum this lane's column": off during warm-up
         mbar_wait_sleep(barFull + 8 * unit, lap, p.backoffNs);           // every piece starts on a unit boundary
-        bool more = true;
-        #pragma unroll 1
-        while (more) {
-            float bodySum0 = 0.f, bodySum1 = 0.f;                        // <= 11 values each per float partial
-            #pragma unroll
-            for (int t = 0; t < kTaps; ++t) {
-                float sv0, sv1;
-                vertical_row<kU16>(t, qab0, qsp0, qab1, qsp1, w2, addr0, addr1, ca, cb, eps2, sv0, sv1);
-                addr0 += kRingRowBytes; addr1 += kRingRowBytes;
-                if (kMap) { stg_f32_if<0>(mapAddr, sv0, pred0); stg_f32_if<128>(mapAddr, sv1, pred1); mapAddr += mapPitchBytes; }
-                bodySum0 += pred0 ? sv0 : 0.f;
-                bodySum1 += pred1 ? sv1 : 0.f;
-                if (__builtin_expect(--n == 0, 0)) {                     // warp-uniform
-                    unitLeft -= step; warmLeft -= step; pieceLeft -= step;
-                    if (warmLeft == 0) { pred0 = colOk0 ? 1u : 0u; pred1 = colOk1 ? 1u : 0u; warmLeft = 0x40000000; }
-                    if (unitLeft == 0 || pieceLeft == 0) {
-                        // done reading the unit (count 32: every lane releases its own loads); a piece that ends inside a
-                        // unit leaves the producer's filler rows unread
-                        mbar_arrive(barEmpty + 8 * unit);
-                        addr0 += (uint32_t)unitLeft * kRingRowBytes; addr1 += (uint32_t)unitLeft * kRingRowBytes;
-                        if (++unit == (uint32_t)G::kRingUnits) { unit = 0; lap ^= 1u; addr0 = ringBase + vOff0; addr1 = ringBase + vOff1; }
-                        unitLeft = kBlkRows;
-                        if (pieceLeft != 0) mbar_wait_sleep(barFull + 8 * unit, lap, p.backoffNs);
-                    }
-                    if (pieceLeft == 0) { more = false; break; }
-                    step = min(unitLeft, min(warmLeft, pieceLeft)); n = step;
+        // The 11 row positions of the unrolled body are entered through a switch on the position the previous run stopped
+        // at, so the event code below exists once, out of line of the row code (inlined after each of the 11 rows it
+        // pushed the hot loops past the instruction cache: no_instruction became the top stall reason).
+        float bodySum0 = 0.f, bodySum1 = 0.f;                            // <= 11 values each per float partial
+        int t = 0;                                                       // position in the 11-row body
+        #define VROW(T)                                                                                                  \
+                {                                                                                                        \
+                    float sv0, sv1;                                                                                      \
+                    vertical_row<kU16>(T, qab0, qsp0, qab1, qsp1, w2, addr0, addr1, ca, cb, eps2, sv0, sv1);             \
+                    addr0 += kRingRowBytes; addr1 += kRingRowBytes;                                                      \
+                    store_and_sum_if<0, kMap != 0>(mapAddr, sv0, pred0, bodySum0);                                       \
+                    if (kMap == 2) store_and_sum_if<0, true>(mapAddr + mapCol1Bytes, sv1, pred1, bodySum1);              \
+                    else           store_and_sum_if<128, kMap != 0>(mapAddr, sv1, pred1, bodySum1);                      \
+                    if (kMap) mapAddr += mapPitchBytes;                                                                  \
+                    if (--n == 0) { t = (T + 1) % kTaps; break; }                                                        \
                 }
+        #pragma unroll 1
+        for (;;) {
+            switch (t) {                                                 // warp-uniform
+                case 0:  total += (double)(bodySum0 + bodySum1); bodySum0 = bodySum1 = 0.f;
+                         VROW(0)
+                case 1:  VROW(1)
+                case 2:  VROW(2)
+                case 3:  VROW(3)
+                case 4:  VROW(4)
+                case 5:  VROW(5)
+                case 6:  VROW(6)
+                case 7:  VROW(7)
+                case 8:  VROW(8)
+                case 9:  VROW(9)
+                default: VROW(10)
+                         t = 0;
+                         continue;                                       // next body, no event in between
             }
-            total += (double)(bodySum0 + bodySum1);
+            // ---- events (n reached 0)
+            unitLeft -= step; warmLeft -= step; pieceLeft -= step;
+            if (warmLeft == 0) { pred0 = colOk0 ? 1u : 0u; pred1 = colOk1 ? 1u : 0u; warmLeft = 0x40000000; }
+            if (unitLeft == 0 || pieceLeft == 0) {
+                // done reading the unit (count 32: every lane releases its own loads); a piece that ends inside a unit
+                // leaves the producer's filler rows unread
+                mbar_arrive(barEmpty + 8 * unit);
+                addr0 += (uint32_t)unitLeft * kRingRowBytes; addr1 += (uint32_t)unitLeft * kRingRowBytes;
+                if (++unit == (uint32_t)G::kRingUnits) { unit = 0; lap ^= 1u; addr0 = ringBase + vOff0; addr1 = ringBase + vOff1; }
+                unitLeft = kBlkRows;
+                if (p.dbgTimes) {                            // development aid: when did this pair finish its k-th ring unit
+                    ++dbgUnits;
+                    if (lane == 0 && dbgUnits + 1 < (uint32_t)kDbgWords) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); p.dbgTimes[kDbgWords * slot + 1 + dbgUnits] = tt; }
+                }
+                if (pieceLeft != 0) mbar_wait_sleep(barFull + 8 * unit, lap, p.backoffNs);
+            }
+            if (pieceLeft == 0) break;
+            step = min(unitLeft, min(warmLeft, pieceLeft)); n = step;
         }
+        #undef VROW
+        total += (double)(bodySum0 + bodySum1);
     }
 
 }
 
-template <bool kMap, bool kU16>
+template <int kMap, bool kU16>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ FusedParams p, const __grid_constant__ ExchangeParams x)
@@ -671,8 +723,9 @@ __global__ void pack_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, co
                                long long step, long long stride, int width, int height)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < height) dst[(long long)y * dstPitch + x] = src[(long long)x * step + (long long)y * stride];
+    if (x >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < height; y += gridDim.y * blockDim.y)     // grid-stride: any height
+        dst[(long long)y * dstPitch + x] = src[(long long)x * step + (long long)y * stride];
 }
 
 // same for 16-bit pixels: src is a byte pointer, step/stride are BYTE distances (multiples of 2)
@@ -680,8 +733,8 @@ __global__ void pack_u16_kernel(uint8_t* __restrict__ dst, long long dstPitch, c
                                 long long step, long long stride, int width, int height)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < height)
+    if (x >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < height; y += gridDim.y * blockDim.y)
         *(uint16_t*)(dst + (long long)y * dstPitch + 2 * x) = *(const uint16_t*)(src + (long long)x * step + (long long)y * stride);
 }
 
@@ -691,34 +744,50 @@ __global__ void pack_luma_kernel(uint8_t* __restrict__ dst, long long dstPitch, 
                                  long long step, long long stride, int width, int height)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < height) {
+    if (x >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < height; y += gridDim.y * blockDim.y) {
         const uint8_t* px = src + (long long)x * step + (long long)y * stride;
         const unsigned r = px[0], g = px[1], b = px[2];
         dst[(long long)y * dstPitch + x] = (uint8_t)((r * 19595u + g * 38470u + b * 7471u + 32768u) >> 16);
     }
 }
 
-// splits an interleaved C-channel image into C dense pitched planes (plane c at dst + c*planeStride) in one read of the bytes
+// splits an interleaved C-channel image into C dense pitched planes (plane c at dst + c*planeStride) in one read of the
+// bytes.  C <= 4: a thread handles 4 neighbouring pixels, i.e. C aligned 32-bit loads and one 32-bit store per plane (rows
+// start 16-byte aligned on both sides); other channel counts go byte by byte.
+template <int kC>
+__global__ void deinterleave4_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, long long planeStride,
+                                        const uint8_t* __restrict__ src, long long srcPitch, int width, int height)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < height; y += gridDim.y * blockDim.y) {
+        const uint32_t* in = (const uint32_t*)(src + (long long)y * srcPitch + (long long)x4 * kC);      // 4*kC bytes = kC words
+        uint32_t w[kC];
+        #pragma unroll
+        for (int i = 0; i < kC; ++i) w[i] = __ldg(in + i);            // reads past `width` stay inside the 16-byte padded row
+        #pragma unroll
+        for (int c = 0; c < kC; ++c) {
+            uint32_t out = 0;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {                             // pixel k, channel c = byte k*kC + c of the group
+                const int byte = k * kC + c;
+                out |= ((w[byte >> 2] >> (8 * (byte & 3))) & 0xffu) << (8 * k);
+            }
+            *(uint32_t*)(dst + c * planeStride + (long long)y * dstPitch + x4) = out;     // plane rows are padded to 16 bytes too
+        }
+    }
+}
+
 __global__ void deinterleave_u8_kernel(uint8_t* __restrict__ dst, long long dstPitch, long long planeStride,
                                        const uint8_t* __restrict__ src, long long srcPitch, int channels, int width, int height)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < height) {
+    if (x >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < height; y += gridDim.y * blockDim.y) {
         const uint8_t* px = src + (long long)y * srcPitch + (long long)x * channels;
         for (int c = 0; c < channels; ++c) dst[c * planeStride + (long long)y * dstPitch + x] = px[c];
     }
-}
-
-// merges C dense float maps (map c at src + c*planeStride) into one interleaved map: dst[y*dstPitch + x*C + c]
-__global__ void interleave_map_kernel(float* __restrict__ dst, long long dstPitch, const float* __restrict__ src, long long srcPitch,
-                                      long long planeStride, int channels, int width, int height)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < height)
-        for (int c = 0; c < channels; ++c) dst[(long long)y * dstPitch + (long long)x * channels + c] = src[c * planeStride + (long long)y * srcPitch + x];
 }
 
 // scatters a dense float map into an arbitrarily strided one (ssimStep != 1, negative ssimStride; src/ssim.cpp:661-667)
@@ -726,16 +795,17 @@ __global__ void scatter_map_kernel(float* __restrict__ dst, long long dstStep, l
                                    const float* __restrict__ src, long long srcPitch, int width, int height)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < height) dst[(long long)x * dstStep + (long long)y * dstStride] = src[(long long)y * srcPitch + x];
+    if (x >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < height; y += gridDim.y * blockDim.y)
+        dst[(long long)x * dstStep + (long long)y * dstStride] = src[(long long)y * srcPitch + x];
 }
 
 __global__ void synth_fill_kernel(uint8_t* __restrict__ dA, long long pitchA, uint8_t* __restrict__ dB, long long pitchB,
                                   int width, int rows, int y0, uint32_t frame, uint64_t seed)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x < width && y < rows) {
+    if (x >= width) return;
+    for (int y = blockIdx.y * blockDim.y + threadIdx.y; y < rows; y += gridDim.y * blockDim.y) {
         uint8_t a, b;
         ssim_synth_pixel(seed, frame, (uint32_t)x, (uint32_t)(y0 + y), &a, &b);
         dA[(long long)y * pitchA + x] = a;
@@ -745,12 +815,18 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ dA, long long pitchA, ui
 
 // ------------------------------------------------------------------------------------------------ launchers
 // cudaFuncSetAttribute is per DEVICE: called from every device context's initialisation (current device = that device)
+template <int kMap, bool kU16>
+static cudaError_t set_smem_attr_one()
+{
+    return cudaFuncSetAttribute(ssim_fused_kernel<kMap, kU16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<kU16>::kCtaSmemBytes);
+}
 static cudaError_t set_smem_attr()
 {
-    cudaError_t e = cudaFuncSetAttribute(ssim_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<false>::kCtaSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ssim_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<false>::kCtaSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ssim_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<true>::kCtaSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ssim_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<true>::kCtaSmemBytes);
+    cudaError_t e = set_smem_attr_one<0, false>();
+    if (e == cudaSuccess) e = set_smem_attr_one<1, false>();
+    if (e == cudaSuccess) e = set_smem_attr_one<2, false>();
+    if (e == cudaSuccess) e = set_smem_attr_one<0, true>();
+    if (e == cudaSuccess) e = set_smem_attr_one<1, true>();
     return e;
 }
 
@@ -760,12 +836,15 @@ cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUte
     if (ctas == 0) return cudaErrorInvalidValue;
     ExchangeParams none;
     if (!xchg) { memset(&none, 0, sizeof(none)); xchg = &none; }
+    const int mapKind = !p.map ? 0 : p.mapStep == 1 ? 1 : 2;
     if (p.u16) {
-        if (p.map) ssim_fused_kernel<true, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else       ssim_fused_kernel<false, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        if (mapKind == 2) return cudaErrorInvalidValue;              // 16-bit pixels: dense maps only
+        if (mapKind) ssim_fused_kernel<1, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        else         ssim_fused_kernel<0, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
     } else {
-        if (p.map) ssim_fused_kernel<true, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else       ssim_fused_kernel<false, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        if (mapKind == 2)      ssim_fused_kernel<2, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        else if (mapKind == 1) ssim_fused_kernel<1, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        else                   ssim_fused_kernel<0, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
     }
     return cudaGetLastError();
 }
@@ -775,22 +854,27 @@ cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm
     cudaError_t e = set_smem_attr();
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<true, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<1, false>)) != cudaSuccess) return e;
     if (regsMap) *regsMap = fa.numRegs;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<false, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<0, false>)) != cudaSuccess) return e;
     if (regsNoMap) *regsNoMap = fa.numRegs;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<true, false>, kCtaThreads, PixGeo<false>::kCtaSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<1, false>, kCtaThreads, PixGeo<false>::kCtaSmemBytes);
     if (e == cudaSuccess) {
         int n16 = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<true, true>, kCtaThreads, PixGeo<true>::kCtaSmemBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<1, true>, kCtaThreads, PixGeo<true>::kCtaSmemBytes);
         if (n16 < n) n = n16;
     }
     if (ctasPerSm) *ctasPerSm = n;
     return e;
 }
 
-static dim3 grid2d(int width, int height, dim3 block) { return dim3((width + block.x - 1) / block.x, (height + block.y - 1) / block.y); }
+// rows go on gridDim.y, which is limited to 65535 blocks: the kernels stride over y, so any height works
+static dim3 grid2d(int width, int height, dim3 block)
+{
+    const unsigned gy = (unsigned)((height + block.y - 1) / block.y);
+    return dim3((width + block.x - 1) / block.x, gy < 65535u ? gy : 65535u);
+}
 
 cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,
                            long long step, long long stride, int width, int height)
@@ -820,15 +904,15 @@ cudaError_t launch_deinterleave_u8(cudaStream_t stream, uint8_t* dst, long long 
                                    long long srcPitch, int channels, int width, int height)
 {
     const dim3 block(64, 4);
-    deinterleave_u8_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, channels, width, height);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_interleave_map(cudaStream_t stream, float* dst, long long dstPitch, const float* src, long long srcPitch,
-                                  long long planeStride, int channels, int width, int height)
-{
-    const dim3 block(64, 4);
-    interleave_map_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, src, srcPitch, planeStride, channels, width, height);
+    // the 4-pixel path reads and writes whole words up to the padded end of a row: both pitches must cover ceil(width/4)*4 pixels
+    const int w4 = (width + 3) / 4;
+    const bool vec = channels <= 4 && (srcPitch & 3) == 0 && (dstPitch & 3) == 0 && srcPitch >= (long long)w4 * 4 * channels && dstPitch >= (long long)w4 * 4 &&
+                     (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)planeStride) & 3) == 0;
+    if (vec && channels == 1)      deinterleave4_u8_kernel<1><<<grid2d(w4, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, width, height);
+    else if (vec && channels == 2) deinterleave4_u8_kernel<2><<<grid2d(w4, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, width, height);
+    else if (vec && channels == 3) deinterleave4_u8_kernel<3><<<grid2d(w4, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, width, height);
+    else if (vec && channels == 4) deinterleave4_u8_kernel<4><<<grid2d(w4, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, width, height);
+    else deinterleave_u8_kernel<<<grid2d(width, height, block), block, 0, stream>>>(dst, dstPitch, planeStride, src, srcPitch, channels, width, height);
     return cudaGetLastError();
 }
 

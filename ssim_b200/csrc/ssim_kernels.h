@@ -17,9 +17,14 @@ constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row
                                    // (tools/dev/tma_probe.cu)
 constexpr int kLoadRows    = 8;    // rows per TMA box (= one horizontal-pass block)
 constexpr int kStages      = 2;    // TMA stages per warp pair
-constexpr int kPairsPerCta = 4;    // warp pairs per CTA: each is one producer warp and one consumer warp
-constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 256: warps 0-3 producers (TMA + horizontal pass), 4-7 consumers
-constexpr int kCtasPerSm   = 2;    // persistent grid: kCtasPerSm x numSMs CTAs, every one resident
+// ONE CTA of 8 warp pairs per SM, not two of 4: with two resident CTAs the warp schedulers serve the CTA that arrived first
+// with priority -- measured (tools/dev/slot_times.py, profiles/r02_slot_times.txt): its pairs ran 2.6x as fast as the second
+// CTA's (1.8 vs 4.7 us per 8-row unit), which then finished alone at 84% of the SM's throughput; which CTA of the grid
+// arrives first on an SM is not a function of blockIdx either.  The warps of one CTA are served evenly (all 8 pairs of a
+// CTA finish within 1% of each other), which is what a static, equal partition of the work needs.
+constexpr int kPairsPerCta = 8;    // warp pairs per CTA: each is one producer warp and one consumer warp
+constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 512: warps 0-7 producers (TMA + horizontal pass), 8-15 consumers
+constexpr int kCtasPerSm   = 1;    // persistent grid: one CTA per SM, every one resident
 constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
 constexpr int kConsumerRegs = 160;
 constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partner warp's mbarrier
@@ -63,6 +68,7 @@ template <bool kU16> struct PixGeo {
 // column's padding units: either way cost = units + 10 for every slot, so all pairs finish together -- no tail, and no
 // halo paid more often than once per slot and once per column.
 constexpr int kPad = 2 * kHalo;
+constexpr int kDbgWords = 32;
 
 struct SlotPlan {
     uint32_t slots;          // warp pairs that get work (<= maxSlots)
@@ -125,10 +131,16 @@ struct SlotGeo {             // the part of FusedParams the cursor needs (kept s
     uint32_t bandsMul, bandsShift;   // n / bands
 };
 
+// units [q0, q1) owned by a slot: equal shares, the first shareR slots hold one unit more
+SSIMK_HD void slot_units(const SlotGeo& g, uint32_t slot, uint32_t& q0, uint32_t& q1)
+{
+    q0 = slot * g.shareQ + (slot < g.shareR ? slot : g.shareR);
+    q1 = q0 + g.shareQ + (slot < g.shareR ? 1u : 0u);
+}
+
 SSIMK_HD void cursor_init(PieceCursor& c, const SlotGeo& g, uint32_t slot)
 {
-    c.q = slot * g.shareQ + (slot < g.shareR ? slot : g.shareR);
-    c.qEnd = c.q + g.shareQ + (slot < g.shareR ? 1u : 0u);
+    slot_units(g, slot, c.q, c.qEnd);
     const uint32_t col = ssimk_div(c.q, g.colMul, g.colShift);
     c.colBase = col * g.colUnits;
     c.frame = (int)ssimk_div(col, g.bandsMul, g.bandsShift);
@@ -159,6 +171,7 @@ struct FusedParams {
     long long pitchA, frameStrideA, pitchB, frameStrideB;
     float*  map;             // NULL when no map is wanted
     long long mapPitch, mapFrameStride;   // floats
+    long long mapStep;       // floats between horizontally adjacent map values (1 = dense rows)
     int width, srcRows, outY0, outRows, frames;
     SlotGeo geo;
     // reduction workspace (per stream): partial sums [slots][entries] (entry e of slot s belongs to frame
@@ -173,6 +186,8 @@ struct FusedParams {
     uint32_t magic;          // 0x4B000000 (float 2^23): kept opaque to ptxas, see the kernel
     uint32_t backoffNs;      // sleep between polls of the partner warp's mbarrier
     float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
+    unsigned long long* dbgTimes;   // development aid (NULL in production): [slots][kDbgWords] globaltimer of each consumer warp: [0] start,
+                                    // [1] end, [1+k] when it finished reading its k-th ring unit (k = 1 .. kDbgWords-2)
 };
 
 // Division of item indices by warp-uniform run-time divisors without the 64-bit division subroutine: keeps the whole item
@@ -230,8 +245,6 @@ cudaError_t launch_pack_luma(cudaStream_t stream, uint8_t* dst, long long dstPit
                              long long step, long long stride, int width, int height);
 cudaError_t launch_deinterleave_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, long long planeStride, const uint8_t* src,
                                    long long srcPitch, int channels, int width, int height);
-cudaError_t launch_interleave_map(cudaStream_t stream, float* dst, long long dstPitch, const float* src, long long srcPitch,
-                                  long long planeStride, int channels, int width, int height);
 cudaError_t launch_scatter_map(cudaStream_t stream, float* dst, long long dstStep, long long dstStride,
                                const float* src, long long srcPitch, int width, int height);
 cudaError_t launch_synth_fill(cudaStream_t stream, uint8_t* dA, long long pitchA, uint8_t* dB, long long pitchB,

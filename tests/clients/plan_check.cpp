@@ -50,7 +50,7 @@ static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_
 
 int main()
 {
-    const uint32_t slots = 148 * 2 * 4;          // B200: 148 SMs x 2 CTAs x 4 warp pairs
+    const uint32_t slots = 148 * 8;              // B200: 148 SMs x one CTA of 8 warp pairs
     const uint32_t widths[] = {1, 63, 64, 65, 640, 1920, 3840, 16384, 100000};
     const uint32_t heights[] = {1, 2, 9, 10, 11, 23, 24, 25, 47, 141, 1080, 2058, 2160, 16384};
     const uint32_t frames[] = {1, 2, 3, 64, 512};

@@ -178,6 +178,12 @@ def test_device_pointers_through_the_reference_api():
     p.ssimMap = None
     assert api.rmgr_lib().rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 0
     assert abs(out.value - float(o)) <= GLOBAL_TOL
+    # interleaved DEVICE map (ssimStep = 3): written in place by the fused kernel, the other two channels stay untouched
+    dM3 = torch.full((H, W, 3), -7.0, dtype=torch.float32, device="cuda")
+    p.ssimMap, p.ssimStep, p.ssimStride = dM3.data_ptr() + 4, 3, 3 * W
+    assert api.rmgr_lib().rmgr_ssim_compute_ssim(C.byref(out), C.byref(p), None) == 0
+    got = dM3.cpu().numpy()
+    assert np.abs(got[..., 1] - om).max() <= PIXEL_TOL and (got[..., 0] == -7.0).all() and (got[..., 2] == -7.0).all()
 
 
 def test_all_channels_in_one_pass(bbb360):

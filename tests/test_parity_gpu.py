@@ -220,6 +220,17 @@ def test_map_only_and_errors():
     assert lib.rmgr_ssim_compute_ssim_openmp(C.byref(out), C.byref(p)) == 0 and out.value == float(s)
 
 
+def test_absurd_size_is_enomem_not_a_crash():
+    """A request whose scratch planes cannot be allocated fails with ENOMEM before any byte of the caller's images is read"""
+    lib = api.cuda_lib()
+    a = np.zeros(64, np.uint8)
+    out = C.c_float()
+    rc = lib.ssim_cuda_compute(0, 2000000000, 2000000000, a.ctypes.data, 1, 2000000000, a.ctypes.data, 1, 2000000000, None, 0, 0, C.byref(out))
+    assert rc == 12, (rc, lib.ssim_cuda_last_error_string())
+    s, _ = api.compute_ssim(*synth_pair(100, 50, 1))            # the library keeps working afterwards
+    assert 0.0 < float(s) < 1.0
+
+
 def test_flat_and_extreme_images():
     """constant images (fp32 cancellation worst case) and full-range noise"""
     for va, vb in [(0, 0), (255, 255), (200, 199), (0, 255), (17, 230)]:
