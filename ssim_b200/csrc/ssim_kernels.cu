@@ -400,10 +400,11 @@ __device__ __forceinline__ uint32_t share_of_unit(const SlotGeo& g, uint32_t q)
 // none of the frame's rows deliver 0) and now arrives at the frame's counter: threadFenceReduction pattern.
 __device__ __forceinline__ void frame_arrive(const FusedParams& p, const ExchangeParams& x, int f, int lane)
 {
-    const uint32_t frameUnits = p.geo.bands * p.geo.colUnits;
+    const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
     const uint32_t u0 = (uint32_t)f * frameUnits, u1 = u0 + frameUnits;
-    // the slots that deliver to this frame are those whose units intersect the frame's: a contiguous run [sLo, sHi]
-    const uint32_t sLo = share_of_unit(p.geo, u0), sHi = share_of_unit(p.geo, u1 - 1u);
+    // the slots that deliver to this frame are the members of the teams whose units intersect the frame's: a contiguous
+    // run [sLo, sHi] (members without a band there deliver zeros)
+    const uint32_t sLo = share_of_unit(p.geo, u0) * p.geo.group, sHi = (share_of_unit(p.geo, u1 - 1u) + 1u) * p.geo.group - 1u;
     __threadfence();
     unsigned prev = 0;
     if (lane == 0) prev = atomicAdd(p.frameDone + f, 1u);
@@ -560,7 +561,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
     uint32_t addr0 = ringBase + vOff0, addr1 = ringBase + vOff1;
 
     // partial sums: one entry per frame this slot's unit range touches, entry index = frame - first such frame
-    const uint32_t frameUnits = p.geo.bands * p.geo.colUnits;
+    const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
     uint32_t q0, qEnd;
     slot_units(p.geo, slot, q0, qEnd);
     if (q0 >= qEnd) return;                                 // an empty share (weighted split of a very short range): nothing to deliver

@@ -1,7 +1,7 @@
 // Host-only check of the persistent kernel's work partition (ssimk::plan_slots + the PieceCursor both warps of a pair
-// run in the kernel): for any shape the pieces of all slots must tile every column's rows exactly once, in order, with
-// pieces of the same slot in increasing (frame, band) order, shares balanced to +-1 unit, and no slot touching more frames
-// than the plan reserved partial-sum entries for.
+// run in the kernel): for any shape the pieces of all slots must tile every band's rows of every frame exactly once, in
+// order, the members of a team must walk the same rows of adjacent bands, shares must be balanced to +-1 unit, and no slot
+// may touch more frames than the plan reserved partial-sum entries for.
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -22,28 +22,38 @@ static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_
     const uint32_t bands = (w + 63) / 64;
     const uint64_t cols = (uint64_t)bands * f;
     expect(plan.slots >= 1 && plan.slots <= maxSlots, "slot count in range", w, h, f, plan.slots);
-    expect((uint64_t)plan.slots * plan.shareQ + plan.shareR == cols * (h + 10), "shares add up to all units", w, h, f, plan.slots);
-    expect(plan.shareQ >= (plan.slots > 1 ? minUnits : 1u), "no slot thinner than minUnits", w, h, f, plan.slots);
+    expect(plan.group >= 1 && plan.group <= 8 && plan.slots % plan.group == 0, "whole teams of 1..8 pairs", w, h, f, plan.slots);
+    const uint32_t teams = plan.slots / plan.group;
+    expect((uint64_t)teams * plan.shareQ + plan.shareR == (uint64_t)g.groupsPerFrame * f * (h + 10), "shares add up to all units", w, h, f, plan.slots);
+    expect(plan.shareQ >= (teams > 1 ? minUnits : 1u), "no team thinner than minUnits", w, h, f, plan.slots);
+    expect((uint64_t)g.groupsPerFrame * plan.group >= bands && (uint64_t)(g.groupsPerFrame - 1) * plan.group < bands, "groups cover the bands", w, h, f, plan.slots);
+    expect((double)bands / ((double)g.groupsPerFrame * plan.group) >= 0.9 || bands < 8, "little ragged waste", w, h, f, plan.slots);
     std::vector<uint32_t> nextRow(cols, 0);          // rows [0, nextRow) of each column are covered so far
     uint64_t lastCol = 0;
     bool first = true;
+    (void)lastCol; (void)first;
     for (uint32_t s = 0; s < plan.slots; ++s) {
         ssimk::PieceCursor c;
         ssimk::cursor_init(c, g, s);
         ssimk::Piece pc;
-        int framesTouched = 0, lastFrame = -1;
+        uint32_t q0, q1;
+        ssimk::slot_units(g, s, q0, q1);
+        const uint32_t frameUnits = g.groupsPerFrame * g.colUnits;
+        expect((q1 - 1) / frameUnits - q0 / frameUnits + 1 <= plan.entries, "entries cover every frame whose units a slot owns", w, h, f, plan.slots);
+        uint64_t prevCol = 0;
+        bool any = false;
         while (ssimk::cursor_next(c, g, pc)) {
             const uint64_t col = (uint64_t)pc.frame * bands + pc.band;
             expect(pc.frame >= 0 && (uint32_t)pc.frame < f && pc.band >= 0 && (uint32_t)pc.band < bands, "piece inside the batch", w, h, f, plan.slots);
-            if (col >= cols) return;
+            if (pc.frame < 0 || (uint32_t)pc.frame >= f || pc.band < 0 || (uint32_t)pc.band >= bands) return;
+            expect((uint32_t)pc.band % plan.group == s % plan.group, "member m of a team takes band group*k + m", w, h, f, plan.slots);
             expect(pc.nOut >= 1 && (uint32_t)(pc.r0 + pc.nOut) <= h, "piece inside its column", w, h, f, plan.slots);
-            expect((uint32_t)pc.r0 == nextRow[col], "pieces of a column are contiguous and in order", w, h, f, plan.slots);
-            expect(first || col >= lastCol, "columns in increasing order across slots", w, h, f, plan.slots);
+            expect((uint32_t)pc.r0 == nextRow[col], "pieces of a band are contiguous and in order over the slots", w, h, f, plan.slots);
+            expect(!any || col > prevCol, "a slot's pieces move forward", w, h, f, plan.slots);
+            expect((uint32_t)pc.frame >= q0 / frameUnits && (uint32_t)pc.frame <= (q1 - 1) / frameUnits, "piece in a frame whose units the slot owns", w, h, f, plan.slots);
             nextRow[col] = (uint32_t)(pc.r0 + pc.nOut);
-            lastCol = col; first = false;
-            if (pc.frame != lastFrame) { ++framesTouched; lastFrame = pc.frame; }
+            prevCol = col; any = true;
         }
-        expect((uint32_t)framesTouched <= plan.entries, "entries cover every frame a slot touches", w, h, f, plan.slots);
     }
     for (uint64_t c = 0; c < cols; ++c) expect(nextRow[c] == h, "every row of every column covered exactly once", w, h, f, plan.slots);
 }
@@ -65,9 +75,11 @@ int main()
     check(1, 3840, 2160, 2, 24);
     // the documented plans
     ssimk::SlotPlan p;
-    ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p);   expect(p.slots == 1184 && p.shareQ == 109 && p.entries == 1, "one 4K pair: 109-110 units per slot", 3840, 2160, 1, p.slots);
-    ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p);  expect(p.slots == 1184 && p.shareQ == 7037, "64 x 4K", 3840, 2160, 64, p.slots);
-    ssimk::plan_slots(slots, 333, 141, 1, 24, &p);     expect(p.slots == 37, "small image: fewer slots", 333, 141, 1, p.slots);
+    ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p);   expect(p.group == 6 && p.slots == 1182 && p.shareQ == 110 && p.entries == 1, "one 4K pair: 197 teams of 6 bands, 110-111 units each", 3840, 2160, 1, p.slots);
+    ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p);  expect(p.group == 6 && p.slots == 1182 && p.shareQ == 7049, "64 x 4K", 3840, 2160, 64, p.slots);
+    ssimk::plan_slots(slots, 16384, 2058, 1, 24, &p);  expect(p.group == 8 && p.slots == 1184, "a 16384-wide strip: one team of 8 bands per CTA", 16384, 2058, 1, p.slots);
+    ssimk::plan_slots(slots, 1920, 1080, 1, 24, &p);   expect(p.group == 6 && p.slots == 1182, "1080p: 5 groups of 6 bands", 1920, 1080, 1, p.slots);
+    ssimk::plan_slots(slots, 333, 141, 1, 24, &p);     expect(p.group == 6 && p.slots == 36, "small image: fewer slots", 333, 141, 1, p.slots);
     ssimk::plan_slots(slots, 8, 8, 1, 24, &p);         expect(p.slots == 1 && p.shareQ == 18, "tiny image: one slot", 8, 8, 1, p.slots);
     expect(!ssimk::plan_slots(slots, 100000, 100000, 100, 24, &p), "more than 2^31 units is refused", 100000, 100000, 100, 0);
     std::printf(fails ? "plan_slots: %d failures\n" : "plan_slots ok\n", fails);

@@ -68,7 +68,7 @@ def test_u16_scale_invariance_pins_the_8_bit_path():
         img = g[name]
         s16, m16 = api.compute_u16(ref.astype(np.uint16) * 257, img.astype(np.uint16) * 257, want_map=True)
         s8, m8 = api.compute_ssim(ref, img, want_map=True)
-        assert abs(float(s16) - float(s8)) <= 2e-7 and np.abs(m16 - m8).max() <= 2e-4
+        assert abs(float(s16) - float(s8)) <= 5e-7 and np.abs(m16 - m8).max() <= 2e-4      # a few float ulps: C1, C2 and the partition of the work round differently
         assert abs(float(s16) - float(golden[name]["golden_double_mean"])) <= GLOBAL_TOL   # the reference's own known answers (tests/rmgr-ssim-tests.cpp:354-359)
 
 
