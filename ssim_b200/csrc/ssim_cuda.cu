@@ -38,7 +38,7 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int  g_lastLaunches = 0;
 std::atomic<int> g_minSlotRows{0};       // tuning knobs (0 = automatic), see ssim_cuda_set_tuning()
-std::atomic<int> g_maxCtasPerSm{0};
+std::atomic<int> g_waveRows{0};
 std::atomic<unsigned long long*> g_dbgTimes{nullptr};   // development aid, see ssim_cuda_debug_slot_times()
 
 int fail(int code, const char* fmt, ...)
@@ -232,7 +232,7 @@ struct Workspace {             // reduction workspace of one stream, see get_wor
 struct Context {
     int device = -1;
     int numSMs = 0;
-    int ctasPerSm = ssimk::kCtasPerSm;
+    int pairsPerSm = ssimk::kPairsFair;       // warp pairs resident per SM
     cudaStream_t stream = nullptr;            // stream of the blocking host-pointer path (compute)
     cudaStream_t streamIn = nullptr;          // pipelined host path: H2D copies
     cudaStream_t streamOut = nullptr;         // pipelined host path: D2H copies
@@ -298,10 +298,10 @@ int create_context(int device, Context** out)
         CU_TRY(cudaEventCreateWithFlags(&c->evDone[i], cudaEventDisableTiming));
     }
     c->chunkSumsHost.pinnedHost = true;
-    int regsMap = 0, regsNoMap = 0, ctas = 0;
-    CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &ctas));
-    // the kernel is persistent: its grid must be resident at once, so never plan for more CTAs per SM than actually fit
-    c->ctasPerSm = std::max(1, std::min(ctas, ssimk::kCtasPerSm));
+    int regsMap = 0, regsNoMap = 0, pairs = 0;
+    CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &pairs));
+    if (pairs < ssimk::kPairsFair) return fail(EIO, "the fused kernel does not fit this device (%d warp pairs per SM)", pairs);
+    c->pairsPerSm = pairs;
     *out = c.release();
     return 0;
 }
@@ -364,15 +364,17 @@ int acquire_host_context(Context** c, std::unique_lock<std::mutex>* lock)
 // See "work partition" in ssim_kernels.h: the persistent grid's warp pairs ("slots") share the rows of all (frame, band)
 // columns evenly.  The only choices left to the host are how many CTAs per SM to use and how thin the work may be spread
 // (a slot pays 10 start-up rows, so tiny inputs use fewer slots).
-const uint32_t kDefaultMinSlotRows = 24;
+const uint32_t kDefaultMinSlotRows = 12;
+const int kDefaultWaveRows = 540;         // share of a warp pair in waves mode (about the 540-row segments r1 measured best)
 
-bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, ssimk::SlotPlan* plan)
+bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, bool singleWave, ssimk::SlotPlan* plan)
 {
-    int ctas = g_maxCtasPerSm.load(std::memory_order_relaxed);
-    if (ctas <= 0 || ctas > c->ctasPerSm) ctas = c->ctasPerSm;
     const int minRows = g_minSlotRows.load(std::memory_order_relaxed);
-    return ssimk::plan_slots((uint32_t)(c->numSMs * ctas * ssimk::kPairsPerCta), width, outRows, frames,
-                             minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan);
+    int waveRows = g_waveRows.load(std::memory_order_relaxed);
+    if (waveRows == 0) waveRows = kDefaultWaveRows;
+    if (waveRows > 0 && waveRows < 64) waveRows = 64;
+    return ssimk::plan_slots((uint32_t)(c->numSMs * c->pairsPerSm), width, outRows, frames,
+                             minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan, singleWave || waveRows < 0 ? 0u : (uint32_t)waveRows);
 }
 
 // Reduction workspace of a stream: per-frame arrival counters (zero between launches: the kernel resets them), then
@@ -427,7 +429,8 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (dMap && mapStep != 1 && elemBytes != 1) return fail(EINVAL, "maps with a pixel step are supported for 8-bit images only");
 
     ssimk::SlotPlan plan;
-    if (!plan_for(c, width, outRows, frames, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
+    // strips exchanged with peers spin on the other GPUs' kernels: keep those launches in a single wave
+    if (!plan_for(c, width, outRows, frames, xchg != nullptr, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
 
     WorkspaceView ws;
     int rc = get_workspace(c, stream, frames, (size_t)plan.slots * plan.entries, &ws);
@@ -438,6 +441,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
 
     ssimk::FusedParams p;
     memset(&p, 0, sizeof(p));
+    p.pairsPerCta = (int)plan.pairsPerCta;
     p.u16 = elemBytes == 2;
     p.a = dA; p.b = dB;
     p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
@@ -1220,9 +1224,9 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
 
 void ssim_cuda_debug_slot_times(unsigned long long* dTimes) { g_dbgTimes.store(dTimes, std::memory_order_relaxed); }
 
-void ssim_cuda_set_tuning(int maxCtasPerSm, int minSlotRows)
+void ssim_cuda_set_tuning(int waveRows, int minSlotRows)
 {
-    g_maxCtasPerSm.store(maxCtasPerSm > 0 ? maxCtasPerSm : 0, std::memory_order_relaxed);
+    g_waveRows.store(waveRows, std::memory_order_relaxed);
     g_minSlotRows.store(minSlotRows > 0 ? minSlotRows : 0, std::memory_order_relaxed);
 }
 

@@ -161,7 +161,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
 }
 
 // mbarriers of a pair (byte offsets from the pair's first barrier)
-constexpr uint32_t kBarTmaFull = 0, kBarStageEmpty = 16, kBarRingFull = 32, kBarRingEmpty = 64;
+constexpr uint32_t kBarTmaFull = 0, kBarStageEmpty = 16, kBarRingFull = 32, kBarRingEmpty = 48;
 
 // ---- producer: TMA + horizontal pass
 template <bool kU16>
@@ -236,19 +236,20 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     // 8-bit: three 16-byte chunks holding columns 16hq-16 .. 16hq+31; 16-bit: 64-byte window holding columns 16hq-8 .. 16hq+23
     const uint32_t hColOff = kU16 ? hq * 32 : hq * 16;
     const uint32_t hSrcOff = hr * kBoxW + hColOff;
-    // Ring position of this lane's row within a unit.  Layout of a ring row (1056 bytes): two planes of 64 packed pairs,
-    // {E_h[a'], E_h[b']} at +0 and {E_h[(a'-b')^2], E_h[a'b']} at +512, then 32 bytes of padding; column c sits at
-    // 8*(c ^ (c>>4)).  Bank-conflict freedom without any per-access arithmetic: in the producer's 8-byte stores a half-warp
-    // is 4 rows x 4 column groups writing the same j -- the XOR by the group index spreads the groups over 4 adjacent slots
-    // and the 32-byte pad moves each following row by 4 slots (16 distinct slots); in the consumer's 8-byte loads a
-    // half-warp reads 16 adjacent columns of one group (XOR by a constant).  The store to column j goes to
-    // dst[j & 3] + 32*(j >> 2).
-    uint32_t laneDst[4];
-    #pragma unroll
-    for (int m = 0; m < 4; ++m) laneDst[m] = ringBase + hr * kRingRowBytes + hq * 128 + ((uint32_t)(m ^ hq) << 3);
+    // Ring: two halves of 11 rows (one half = one consumer body), a full/empty mbarrier each.  Input row i of a piece lives
+    // in half (firstHalf + i / 11) & 1 at row t = i % 11 (every piece starts a new half).  Layout of a ring row (1056 bytes):
+    // two planes of 64 packed pairs, {E_h[a'], E_h[b']} at +0 and {E_h[(a'-b')^2], E_h[a'b']} at +512, then 32 bytes of
+    // padding; column c sits at 8*(c ^ (c>>4)).  Bank-conflict freedom without any per-access arithmetic: in the producer's
+    // 8-byte stores a half-warp is 4 rows x 4 column groups writing the same j -- the XOR by the group index spreads the
+    // groups over 4 adjacent slots and the 32-byte pad moves each following row by 4 slots (16 distinct slots); in the
+    // consumer's 8-byte loads a half-warp reads 16 adjacent columns of one group (XOR by a constant).  Both sides address
+    // "register + immediate": the store to column j goes to dst[j & 3] + 32*(j >> 2), the load of row t comes from
+    // base + 1056*t.
 
     uint32_t gblk = 0;                                      // blocks computed so far
-    uint32_t unit = 0, lapParity = 0;                       // ring unit block gblk goes to, parity of the ring lap it belongs to
+    uint32_t firstHalf = 0;                                 // ring halves (global count) used by the pieces before this one
+    uint32_t acquired = 0;                                  // ring halves (global count) this warp may write
+    uint32_t released = 0;                                  // ring halves (global count) handed to the consumer
     #pragma unroll 1
     for (;;) {
         // (a - ca, b - cb) from the bytes: PRMT builds 2^23 + byte, one packed FADD removes 2^23 + centre (exact)
@@ -319,7 +320,13 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             // drained and lane 0 never spins)
             mbar_arrive(barStageEmpty + 8 * stage);
 
-            const uint32_t unitOff = unit * kRingUnitBytes;
+            // ring position of this lane's row (see above)
+            const uint32_t i  = (uint32_t)blk * kBlkRows + hr;
+            const uint32_t ih = i / kTaps, t = i - ih * kTaps;
+            const uint32_t dstRow = ringBase + (((firstHalf + ih) & 1u) * kTaps + t) * kRingRowBytes + hq * 128;
+            uint32_t dst4[4];
+            #pragma unroll
+            for (int m = 0; m < 4; ++m) dst4[m] = dstRow + ((uint32_t)(m ^ hq) << 3);
 
             u64 hab[16], hsp[16];
             #pragma unroll
@@ -353,23 +360,33 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
                     // refill this block's stage with the block two ahead (all lanes have released it above)
                     if (blk + kStages < g.nBlk) issue(g, blk + kStages, stage, true, (gblk >> 1) & 1u, patched);
                     else if (haveN)             issue(gN, blk + kStages - g.nBlk, stage, true, (gblk >> 1) & 1u, patched);
-                    // first store of the block: the ring unit must have been drained by the consumer (waiting here, not at the
-                    // top, lets the loads and the first 10 columns of math overlap the wait); parity of the previous lap --
-                    // the first lap passes at once on the fresh barrier
-                    mbar_wait_sleep(barEmpty + 8 * unit, lapParity ^ 1u, p.backoffNs);
+                    // first store of the block: the ring halves this block touches must have been drained by the consumer
+                    // (waiting here, not at the top, lets the loads and the first 10 columns of math overlap the wait); parity
+                    // of the half's previous use -- its first use passes at once on the fresh barrier.  A piece's last block
+                    // may spill filler rows into the half after the piece's last one: that is the next piece's first half,
+                    // acquired here already and simply overwritten by it.
+                    const uint32_t lastHalf = firstHalf + ((uint32_t)blk * kBlkRows + kBlkRows - 1) / kTaps;
+                    while (acquired <= lastHalf) {
+                        mbar_wait_sleep(barEmpty + 8 * (acquired & 1u), ((acquired >> 1) & 1u) ^ 1u, p.backoffNs);
+                        ++acquired;
+                    }
                 }
                 if (ii >= 10) {                                         // output j = ii-10 is complete
                     const int j = ii - 10;
-                    const uint32_t dst = laneDst[j & 3] + unitOff + 32 * (j >> 2);
+                    const uint32_t dst = dst4[j & 3] + 32 * (j >> 2);
                     sts64(dst, hab[j]);
                     sts64(dst + kRingPlaneBytes, hsp[j]);
                 }
             }
-            // every lane arrives (barrier count 32): each lane's release covers its own stores, no reliance on warp-level cumulativity
-            mbar_arrive(barFull + 8 * unit);
+            // every lane arrives (barrier count 32): each lane's release covers its own stores, no reliance on warp-level
+            // cumulativity.  Halves completely written so far; the piece's last block also completes its last, partial half.
+            const uint32_t nBodies = ((uint32_t)g.nRows + kTaps - 1) / kTaps;
+            const uint32_t complete = firstHalf + (blk + 1 == g.nBlk ? nBodies : min(((uint32_t)blk * kBlkRows + kBlkRows) / kTaps, nBodies));
+            for (uint32_t h = released; h < complete; ++h) mbar_arrive(barFull + 8 * (h & 1u));
+            released = max(released, complete);
             ++gblk;
-            if (++unit == (uint32_t)G::kRingUnits) { unit = 0; lapParity ^= 1u; }
         }
+        firstHalf += ((uint32_t)g.nRows + kTaps - 1) / kTaps;
         if (!haveN) break;
         g = gN; ca = caN; cb = cbN;
         Piece pc;
@@ -555,22 +572,21 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
 
     const unsigned long long mapPitchBytes = (unsigned long long)p.mapPitch * sizeof(float);
     const unsigned long long mapCol1Bytes = (unsigned long long)p.mapStep * 32 * sizeof(float);      // kMap == 2: this lane's second column
-    // ring position (warp-uniform): the unit being read, the parity of the ring lap it belongs to, and this lane's two
-    // shared-memory addresses of the next row (they advance by one ring row per input row; wrapping happens at unit ends)
-    uint32_t unit = 0, lap = 0;
-    uint32_t addr0 = ringBase + vOff0, addr1 = ringBase + vOff1;
+    // ring: this lane's two column addresses in half 0; the half of body number `gbody` (counted over all pieces of the slot) is
+    // gbody & 1, rows of a body sit at +1056*t (static offsets: the unrolled body is exactly one half)
+    const uint32_t col0Base = ringBase + vOff0, col1Base = ringBase + vOff1;
+    uint32_t gbody = 0;
 
     // partial sums: one entry per frame this slot's unit range touches, entry index = frame - first such frame
     const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
     uint32_t q0, qEnd;
     slot_units(p.geo, slot, q0, qEnd);
-    if (q0 >= qEnd) return;                                 // an empty share (weighted split of a very short range): nothing to deliver
+    if (q0 >= qEnd) return;
     const int fFirst = (int)(q0 / frameUnits), fLast = (int)((qEnd - 1u) / frameUnits);
     double* myPart = p.partials + (size_t)slot * p.entries;
     int curFrame = fFirst;                                  // frames below this one have been delivered
     double total = 0.0;                                     // this lane's sum of curFrame's values so far
 
-    uint32_t dbgUnits = 0;
     if (p.dbgTimes && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbgTimes[kDbgWords * slot] = t; }
     PieceCursor cur;
     cursor_init(cur, p.geo, slot);
@@ -603,6 +619,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
         piece_centre<kU16>(p, g, ca, cb);
         const bool colOk0 = g.bx + lane < p.width;
         const bool colOk1 = g.bx + 32 + lane < p.width;
+        const bool fullBand = g.bx + kBandW <= p.width;                 // warp-uniform: no column predicates needed
         // Map addressing: one 64-bit per-lane address that advances by the pitch per input row (starts 10 rows above the
         // piece, never dereferenced there); the second column is an immediate offset.  Stores are written in PTX so
         // that the address arithmetic stays these two adds per row.
@@ -610,74 +627,47 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
         if (kMap == 1) mapAddr = (unsigned long long)(p.map + (long long)g.frame * p.mapFrameStride + (long long)(pc.r0 - 2 * kHalo) * p.mapPitch + g.bx + lane);
         if (kMap == 2) mapAddr = (unsigned long long)(p.map + (long long)g.frame * p.mapFrameStride + (long long)(pc.r0 - 2 * kHalo) * p.mapPitch + (long long)(g.bx + lane) * p.mapStep);
 
-        // Per-row bookkeeping is ONE countdown: n = rows until the next event, the events being the end of the ring unit
-        // (release it, acquire the next one), the end of the 10 warm-up rows (outputs become valid) and the end of the
-        // piece; everything else about a row is static.
-        int unitLeft = kBlkRows, warmLeft = 2 * kHalo, pieceLeft = g.nRows;
-        int step = min(unitLeft, min(warmLeft, pieceLeft)), n = step;
-        uint32_t pred0 = 0, pred1 = 0;                                   // "store and sum this lane's column": off during warm-up
-        mbar_wait_sleep(barFull + 8 * unit, lap, p.backoffNs);           // every piece starts on a unit boundary
-        // The 11 row positions of the unrolled body are entered through a switch on the position the previous run stopped
-        // at, so the event code below exists once, out of line of the row code (inlined after each of the 11 rows it
-        // pushed the hot loops past the instruction cache: no_instruction became the top stall reason).
-        float bodySum0 = 0.f, bodySum1 = 0.f;                            // <= 11 values each per float partial
-        int t = 0;                                                       // position in the 11-row body
-        #define VROW(T)                                                                                                  \
-                {                                                                                                        \
-                    float sv0, sv1;                                                                                      \
-                    vertical_row<kU16>(T, qab0, qsp0, qab1, qsp1, w2, addr0, addr1, ca, cb, eps2, sv0, sv1);             \
-                    addr0 += kRingRowBytes; addr1 += kRingRowBytes;                                                      \
-                    store_and_sum_if<0, kMap != 0>(mapAddr, sv0, pred0, bodySum0);                                       \
-                    if (kMap == 2) store_and_sum_if<0, true>(mapAddr + mapCol1Bytes, sv1, pred1, bodySum1);              \
-                    else           store_and_sum_if<128, kMap != 0>(mapAddr, sv1, pred1, bodySum1);                      \
-                    if (kMap) mapAddr += mapPitchBytes;                                                                  \
-                    if (--n == 0) { t = (T + 1) % kTaps; break; }                                                        \
-                }
+        // The piece is consumed in bodies of 11 rows = one ring half each; the last body may run past the piece's rows: what
+        // it then reads are stale ring rows, what it computes from them belongs to output rows that are never stored.
+        const int nRows = g.nRows;                                      // input rows that complete a wanted output
+        const int nBodies = (nRows + kTaps - 1) / kTaps;
         #pragma unroll 1
-        for (;;) {
-            switch (t) {                                                 // warp-uniform
-                case 0:  total += (double)(bodySum0 + bodySum1); bodySum0 = bodySum1 = 0.f;
-                         VROW(0)
-                case 1:  VROW(1)
-                case 2:  VROW(2)
-                case 3:  VROW(3)
-                case 4:  VROW(4)
-                case 5:  VROW(5)
-                case 6:  VROW(6)
-                case 7:  VROW(7)
-                case 8:  VROW(8)
-                case 9:  VROW(9)
-                default: VROW(10)
-                         t = 0;
-                         continue;                                       // next body, no event in between
-            }
-            // ---- events (n reached 0)
-            unitLeft -= step; warmLeft -= step; pieceLeft -= step;
-            if (warmLeft == 0) { pred0 = colOk0 ? 1u : 0u; pred1 = colOk1 ? 1u : 0u; warmLeft = 0x40000000; }
-            if (unitLeft == 0 || pieceLeft == 0) {
-                // done reading the unit (count 32: every lane releases its own loads); a piece that ends inside a unit
-                // leaves the producer's filler rows unread
-                mbar_arrive(barEmpty + 8 * unit);
-                addr0 += (uint32_t)unitLeft * kRingRowBytes; addr1 += (uint32_t)unitLeft * kRingRowBytes;
-                if (++unit == (uint32_t)G::kRingUnits) { unit = 0; lap ^= 1u; addr0 = ringBase + vOff0; addr1 = ringBase + vOff1; }
-                unitLeft = kBlkRows;
-                if (p.dbgTimes) {                            // development aid: when did this pair finish its k-th ring unit
-                    ++dbgUnits;
-                    if (lane == 0 && dbgUnits + 1 < (uint32_t)kDbgWords) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); p.dbgTimes[kDbgWords * slot + 1 + dbgUnits] = tt; }
+        for (int body = 0; body < nBodies; ++body, ++gbody) {
+            const uint32_t halfOff = (gbody & 1u) * (kTaps * kRingRowBytes);
+            const uint32_t col0 = col0Base + halfOff, col1 = col1Base + halfOff;
+            mbar_wait_sleep(barFull + 8 * (gbody & 1u), (gbody >> 1) & 1u, p.backoffNs);
+            const int iBase = body * kTaps;
+            float bodySum0 = 0.f, bodySum1 = 0.f;
+            #pragma unroll
+            for (int t = 0; t < kTaps; ++t) {
+                float sv0, sv1;
+                vertical_row<kU16>(t, qab0, qsp0, qab1, qsp1, w2, col0 + t * kRingRowBytes, col1 + t * kRingRowBytes, ca, cb, eps2, sv0, sv1);
+                if (t == kTaps - 1) mbar_arrive(barEmpty + 8 * (gbody & 1u));   // this lane is done reading the half (count 32)
+                const int i = iBase + t;
+                if (i >= 2 * kHalo && i < nRows) {                      // warp-uniform: the row completes a wanted output
+                    if (kMap == 1) {
+                        if (fullBand) { stg_f32<0>(mapAddr, sv0); stg_f32<128>(mapAddr, sv1); }
+                        else {
+                            if (colOk0) stg_f32<0>(mapAddr, sv0);
+                            if (colOk1) stg_f32<128>(mapAddr, sv1);
+                        }
+                    }
+                    if (kMap == 2) {
+                        if (colOk0) stg_f32<0>(mapAddr, sv0);
+                        if (colOk1) stg_f32<0>(mapAddr + mapCol1Bytes, sv1);
+                    }
+                    bodySum0 += sv0; bodySum1 += sv1;
                 }
-                if (pieceLeft != 0) mbar_wait_sleep(barFull + 8 * unit, lap, p.backoffNs);
+                if (kMap) mapAddr += mapPitchBytes;
             }
-            if (pieceLeft == 0) break;
-            step = min(unitLeft, min(warmLeft, pieceLeft)); n = step;
+            const float bodySum = (colOk0 ? bodySum0 : 0.f) + (colOk1 ? bodySum1 : 0.f);
+            total += (double)bodySum;                                   // <= 22 values per float partial
         }
-        #undef VROW
-        total += (double)(bodySum0 + bodySum1);
     }
-
 }
 
-template <int kMap, bool kU16>
-__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
+template <int kMap, bool kU16, int kPairsPerCta>
+__global__ void __launch_bounds__(2 * kPairsPerCta * 32, 8 / kPairsPerCta)
 ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ FusedParams p, const __grid_constant__ ExchangeParams x)
 {
@@ -693,7 +683,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int pr = 0; pr < kPairsPerCta; ++pr)
-            for (int i = 0; i < 12; ++i) mbar_init(smem_u32(&bars[pr][i]), i < kStages ? 1 : 32);   // TMA barriers: 1 arrival; stage-empty, ring full/empty: all 32 lanes
+            for (int i = 0; i < kBarsPerPair; ++i) mbar_init(smem_u32(&bars[pr][i]), i < kStages ? 1 : 32);   // TMA barriers: 1 arrival; stage-empty, ring full/empty: all 32 lanes
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -816,57 +806,78 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ dA, long long pitchA, ui
 
 // ------------------------------------------------------------------------------------------------ launchers
 // cudaFuncSetAttribute is per DEVICE: called from every device context's initialisation (current device = that device)
-template <int kMap, bool kU16>
+template <int kMap, bool kU16, int kPairs>
 static cudaError_t set_smem_attr_one()
 {
-    return cudaFuncSetAttribute(ssim_fused_kernel<kMap, kU16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<kU16>::kCtaSmemBytes);
+    return cudaFuncSetAttribute(ssim_fused_kernel<kMap, kU16, kPairs>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairs * PixGeo<kU16>::kPairSmemBytes);
+}
+template <int kPairs>
+static cudaError_t set_smem_attr_shape()
+{
+    cudaError_t e = set_smem_attr_one<0, false, kPairs>();
+    if (e == cudaSuccess) e = set_smem_attr_one<1, false, kPairs>();
+    if (e == cudaSuccess) e = set_smem_attr_one<2, false, kPairs>();
+    if (e == cudaSuccess) e = set_smem_attr_one<0, true, kPairs>();
+    if (e == cudaSuccess) e = set_smem_attr_one<1, true, kPairs>();
+    return e;
 }
 static cudaError_t set_smem_attr()
 {
-    cudaError_t e = set_smem_attr_one<0, false>();
-    if (e == cudaSuccess) e = set_smem_attr_one<1, false>();
-    if (e == cudaSuccess) e = set_smem_attr_one<2, false>();
-    if (e == cudaSuccess) e = set_smem_attr_one<0, true>();
-    if (e == cudaSuccess) e = set_smem_attr_one<1, true>();
+    cudaError_t e = set_smem_attr_shape<kPairsFair>();
+    if (e == cudaSuccess) e = set_smem_attr_shape<kPairsWave>();
     return e;
 }
 
-cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams* xchg)
+template <int kMap, bool kU16, int kPairs>
+static void launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams& x)
 {
-    const unsigned ctas = (p.geo.slots + kPairsPerCta - 1) / kPairsPerCta;
-    if (ctas == 0) return cudaErrorInvalidValue;
-    ExchangeParams none;
-    if (!xchg) { memset(&none, 0, sizeof(none)); xchg = &none; }
+    const unsigned ctas = (p.geo.slots + kPairs - 1) / kPairs;
+    ssim_fused_kernel<kMap, kU16, kPairs><<<ctas, 2 * kPairs * 32, kPairs * PixGeo<kU16>::kPairSmemBytes, stream>>>(tmA, tmB, p, x);
+}
+template <int kPairs>
+static cudaError_t launch_shape(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams& x)
+{
     const int mapKind = !p.map ? 0 : p.mapStep == 1 ? 1 : 2;
     if (p.u16) {
         if (mapKind == 2) return cudaErrorInvalidValue;              // 16-bit pixels: dense maps only
-        if (mapKind) ssim_fused_kernel<1, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else         ssim_fused_kernel<0, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        if (mapKind) launch_one<1, true, kPairs>(stream, tmA, tmB, p, x);
+        else         launch_one<0, true, kPairs>(stream, tmA, tmB, p, x);
     } else {
-        if (mapKind == 2)      ssim_fused_kernel<2, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else if (mapKind == 1) ssim_fused_kernel<1, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else                   ssim_fused_kernel<0, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        if (mapKind == 2)      launch_one<2, false, kPairs>(stream, tmA, tmB, p, x);
+        else if (mapKind == 1) launch_one<1, false, kPairs>(stream, tmA, tmB, p, x);
+        else                   launch_one<0, false, kPairs>(stream, tmA, tmB, p, x);
     }
     return cudaGetLastError();
 }
 
-cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm)
+cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams* xchg)
+{
+    if (p.geo.slots == 0) return cudaErrorInvalidValue;
+    ExchangeParams none;
+    if (!xchg) { memset(&none, 0, sizeof(none)); xchg = &none; }
+    if (p.pairsPerCta == kPairsWave) return launch_shape<kPairsWave>(stream, tmA, tmB, p, *xchg);
+    if (p.pairsPerCta == kPairsFair) return launch_shape<kPairsFair>(stream, tmA, tmB, p, *xchg);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* pairsPerSm)
 {
     cudaError_t e = set_smem_attr();
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<1, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<1, false, kPairsFair>)) != cudaSuccess) return e;
     if (regsMap) *regsMap = fa.numRegs;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<0, false>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<0, false, kPairsFair>)) != cudaSuccess) return e;
     if (regsNoMap) *regsNoMap = fa.numRegs;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<1, false>, kCtaThreads, PixGeo<false>::kCtaSmemBytes);
-    if (e == cudaSuccess) {
-        int n16 = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<1, true>, kCtaThreads, PixGeo<true>::kCtaSmemBytes);
-        if (n16 < n) n = n16;
-    }
-    if (ctasPerSm) *ctasPerSm = n;
+    // warp pairs resident per SM: the smaller of the two shapes' occupancies (8 for both by construction)
+    int nFair = 0, nWave = 0, n16 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nFair, ssim_fused_kernel<1, false, kPairsFair>, 2 * kPairsFair * 32, kPairsFair * PixGeo<false>::kPairSmemBytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nWave, ssim_fused_kernel<1, false, kPairsWave>, 2 * kPairsWave * 32, kPairsWave * PixGeo<false>::kPairSmemBytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<1, true, kPairsFair>, 2 * kPairsFair * 32, kPairsFair * PixGeo<true>::kPairSmemBytes);
+    int pairs = nFair * kPairsFair;
+    if (nWave * kPairsWave < pairs) pairs = nWave * kPairsWave;
+    if (n16 * kPairsFair < pairs) pairs = n16 * kPairsFair;
+    if (pairsPerSm) *pairsPerSm = pairs;
     return e;
 }
 

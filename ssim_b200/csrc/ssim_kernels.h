@@ -17,23 +17,27 @@ constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row
                                    // (tools/dev/tma_probe.cu)
 constexpr int kLoadRows    = 8;    // rows per TMA box (= one horizontal-pass block)
 constexpr int kStages      = 2;    // TMA stages per warp pair
-// ONE CTA of 8 warp pairs per SM, not two of 4: with two resident CTAs the warp schedulers serve the CTA that arrived first
-// with priority -- measured (tools/dev/slot_times.py, profiles/r02_slot_times.txt): its pairs ran 2.6x as fast as the second
-// CTA's (1.8 vs 4.7 us per 8-row unit), which then finished alone at 84% of the SM's throughput; which CTA of the grid
-// arrives first on an SM is not a function of blockIdx either.  The warps of one CTA are served evenly (all 8 pairs of a
-// CTA finish within 1% of each other), which is what a static, equal partition of the work needs.
-constexpr int kPairsPerCta = 8;    // warp pairs per CTA: each is one producer warp and one consumer warp
-constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 512: warps 0-7 producers (TMA + horizontal pass), 8-15 consumers
-constexpr int kCtasPerSm   = 1;    // persistent grid: one CTA per SM, every one resident
+// Two CTA shapes, 16 warps per SM either way (measured, tools/dev/slot_times.py and profiles/r02_cta_shapes.txt):
+//   * two CTAs of 4 warp pairs (256 threads): the warp schedulers serve the CTA that arrived first on an SM with priority --
+//     its pairs run 2.2x as fast as those of the second CTA (1.8 vs 3.9 us per 8 rows on 4K batches) -- and the SM as a whole
+//     gets 7% MORE done than with evenly served warps (3.26 vs 3.03 blocks/us): the favoured pairs hardly ever wait for an
+//     issue slot, the others fill the gaps.  Good for throughput, fatal for a static partition (the second CTAs finish 45%
+//     later), so this shape is used with MANY more CTAs than fit at once: each CTA does a modest share and the hardware's
+//     block scheduler hands the next CTA to whichever SM has room -- dynamic load balancing for free.
+//   * one CTA of 8 warp pairs (512 threads): the warps of one CTA are served evenly (all 8 pairs finish within 1%), which is
+//     what a single wave needs: small and medium inputs, where every pair gets exactly one equal share.
+constexpr int kPairsWave   = 4;    // warp pairs per CTA in the many-CTAs ("waves") mode
+constexpr int kPairsFair   = 8;    // warp pairs per CTA in the single-wave mode
 constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
 constexpr int kConsumerRegs = 160;
 constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partner warp's mbarrier
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
 constexpr int kRingRowPad     = 32;                      // consecutive rows start 8 banks apart: see the ring layout in the kernel
 constexpr int kRingRowBytes   = 2 * kRingPlaneBytes + kRingRowPad;   // 1056: {E[a'], E[b']} plane, {E[(a'-b')^2], E[a'b']} plane, pad
-constexpr int kRingUnitBytes  = kBlkRows * kRingRowBytes;            // 8448: one producer block = one hand-over unit
 constexpr int kTaps           = 11;
-constexpr int kBarsPerPair    = 16;                      // mbarriers per pair (128 bytes): tmaFull[2] stageEmpty[2] ringFull[4] ringEmpty[4]
+constexpr int kRingRows       = 2 * kTaps;               // 22: two halves of 11 rows; the consumer's unrolled body is exactly one half
+constexpr int kRingBytes      = kRingRows * kRingRowBytes; // 23232
+constexpr int kBarsPerPair    = 8;                       // mbarriers per pair (64 bytes): tmaFull[2] stageEmpty[2] ringFull[2] ringEmpty[2]
 
 // Per pixel type geometry of the TMA stage and the depth of the ring (everything after the widening is identical).
 //   8-bit : box rows of 96 bytes = 16 left margin + 64 columns + 16 right margin; a stage (8 rows of A, 8 rows of B) is 1536
@@ -49,16 +53,12 @@ template <bool kU16> struct PixGeo {
     static constexpr int kBoxLeftElems  = kBoxLeft / kPixBytes;             // 16 / 8
     static constexpr int kImgStageBytes = kBoxBytes * kLoadRows;            // 768 / 1280
     static constexpr int kStageBytes    = 2 * kImgStageBytes;               // 1536 / 2560
-    static constexpr int kRingUnits     = kU16 ? 2 : 3;
-    static constexpr int kRingRows      = kRingUnits * kBlkRows;            // 24 / 16
-    static constexpr int kRingBytes     = kRingUnits * kRingUnitBytes;      // 25344 / 16896
-    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 28416 / 22016
-    static constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;    // 113664 / 88064 (2 CTAs per SM either way)
+    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 26368 / 28416: 8 pairs per SM
 };
 
 // ---- work partition --------------------------------------------------------------------------------------------------
-// The kernel is persistent: `slots` warp pairs (at most kCtasPerSm x numSMs x kPairsPerCta, all resident at once) share
-// the work evenly and statically.  Pairs work in TEAMS of `group` (1..8) pairs with consecutive slot numbers: a team walks
+// `slots` warp pairs share the work evenly and statically (single-wave mode: at most 8 x numSMs of them, all resident at
+// once; waves mode: many more, served by the hardware's block scheduler as CTAs retire).  Pairs work in TEAMS of `group` (1..8) pairs with consecutive slot numbers: a team walks
 // down `group` ADJACENT 64-pixel bands side by side, member m taking band group*k + m, all members over the same rows.
 // (Neighbouring bands share the 16-byte margins of their TMA boxes, i.e. sectors and DRAM atoms; pairs that reach the same
 // rows at unrelated times each fetch them from DRAM again.  Measured with every pair on its own: 4.0x the algorithmic DRAM
@@ -77,16 +77,21 @@ constexpr int kPad = 2 * kHalo;
 constexpr int kDbgWords = 32;
 
 struct SlotPlan {
-    uint32_t slots;          // warp pairs that get work (<= maxSlots) = teams * group
+    uint32_t pairsPerCta;    // kPairsFair (single wave, one CTA per SM) or kPairsWave (many CTAs, two per SM at a time)
+    uint32_t slots;          // warp pairs that get work = teams * group
     uint32_t group;          // pairs per team = adjacent bands walked side by side
     uint32_t shareQ, shareR; // units per team: team j owns shareQ + (j < shareR) units
     uint32_t colUnits;       // units per column = outRows + kPad
     uint32_t entries;        // partial-sum entries per slot = max number of frames whose units one slot can own
 };
 
-// Pure host logic (unit-tested on the CPU: tests/clients/plan_check.cpp).  minUnits: do not spread the work thinner than
-// this many units per slot (tiny images would otherwise pay 10 start-up rows for a handful of output rows per slot).
-inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint32_t frames, uint32_t minUnits, SlotPlan* plan)
+// Pure host logic (unit-tested on the CPU: tests/clients/plan_check.cpp).  maxSlots: warp pairs resident at once (8 per SM).
+// minUnits: do not spread the work thinner than this many units per slot (tiny images would otherwise pay 10 start-up rows
+// for a handful of output rows per slot).  waveUnits: when every resident pair would get at least 3 x waveUnits units the
+// work is cut into shares of about waveUnits units instead and run in waves of 4-pair CTAs (0 = never); the share is
+// nudged so that the last wave of CTAs is nearly full.
+inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint32_t frames, uint32_t minUnits, SlotPlan* plan,
+                       uint32_t waveUnits = 0)
 {
     const unsigned long long bands = ((unsigned long long)width + kBandW - 1) / kBandW;
     const unsigned long long colUnits = (unsigned long long)outRows + kPad;
@@ -108,6 +113,24 @@ inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint
     unsigned long long teams = units / minUnits;
     if (teams > maxSlots / group) teams = maxSlots / group;
     if (teams < 1) teams = 1;
+    plan->pairsPerCta = kPairsFair;
+    if (waveUnits > 0 && units / teams >= 3ull * waveUnits) {
+        // waves mode: among the team counts that give shares of 0.75 .. 1.5 x waveUnits pick the one that wastes the least of
+        // the last wave (resident CTAs = maxSlots / kPairsWave) -- cost = waves x (share + start-up), a partly filled last
+        // wave counting in proportion
+        const unsigned long long resident = maxSlots / kPairsWave;
+        unsigned long long bestTeams = units / waveUnits;
+        double best = 1e300;
+        for (unsigned long long t = units / (waveUnits + waveUnits / 2) + 1; t <= units / (waveUnits - waveUnits / 4); ++t) {
+            const unsigned long long ctas = (t * group + kPairsWave - 1) / kPairsWave;
+            const double waves = (double)(ctas / resident) + ((ctas % resident) ? 0.35 + 0.65 * (double)(ctas % resident) / (double)resident : 0.0);
+            const double cost = waves * ((double)(units / t) + kPad + 12);
+            if (cost < best) { best = cost; bestTeams = t; }
+            if (t - units / (waveUnits + waveUnits / 2) > 4096) break;      // plenty of candidates seen
+        }
+        teams = bestTeams;
+        plan->pairsPerCta = kPairsWave;
+    }
     plan->slots = (uint32_t)(teams * group);
     plan->group = (uint32_t)group;
     plan->shareQ = (uint32_t)(units / teams);
@@ -188,6 +211,7 @@ SSIMK_HD bool cursor_next(PieceCursor& c, const SlotGeo& g, Piece& pc)
 }
 
 struct FusedParams {
+    int pairsPerCta;         // CTA shape: kPairsFair or kPairsWave (SlotPlan::pairsPerCta)
     int u16;                 // 0: 8-bit pixels, 1: 16-bit pixels (pitches and frame strides stay in BYTES)
     const uint8_t* a;        // raw planes (used only to fetch the per-piece centring pixel)
     const uint8_t* b;
@@ -255,10 +279,10 @@ struct ExchangeParams {
 };
 
 // ONE launch per call: TMA loads, both filter passes, the formula, the map, the per-frame reduction and (xchg != NULL) the
-// cross-GPU sum.  The grid is ceil(p.geo.slots / kPairsPerCta) CTAs, all resident.
+// cross-GPU sum.  The grid is ceil(p.geo.slots / p.pairsPerCta) CTAs.
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams* xchg);
 // per-device preparation (sets the dynamic shared-memory limit on the CURRENT device) + kernel facts
-cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* ctasPerSm);
+cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* pairsPerSm);
 
 // layout helpers
 cudaError_t launch_pack_u8(cudaStream_t stream, uint8_t* dst, long long dstPitch, const uint8_t* src,

@@ -109,16 +109,25 @@ def test_many_frames_are_reduced_per_frame(shape):
 
 
 def test_tuning_knobs_do_not_change_results():
-    """ssim_cuda_set_tuning: any slot count gives the same map values up to the per-piece centring (different pieces, same math)"""
-    W, H = 640, 360
-    a, b = synth_pair(W, H, 12)
-    o, _, om = oracle.oracle_ssim(a, b, want_map=True)
+    """ssim_cuda_set_tuning: any partition of the work (single wave of 8-pair CTAs or waves of 4-pair CTAs, any share size)
+    gives the same map values up to the per-piece centring (different pieces, same math)"""
     lib = api.cuda_lib()
     try:
-        for ctas, rows in ((1, 0), (2, 200), (1, 5000), (0, 1), (0, 0)):
-            lib.ssim_cuda_set_tuning(ctas, rows)
-            s, m = api.compute_ssim(a, b, want_map=True)
-            assert abs(float(s) - float(o)) <= GLOBAL_TOL and np.abs(m - om).max() <= PIXEL_TOL, (ctas, rows)
+        for (W, H, F) in ((640, 360, 1), (1920, 1080, 3)):
+            a = np.stack([synth_pair(W, H, 12 + f)[0] for f in range(F)])
+            b = np.stack([synth_pair(W, H, 12 + f)[1] for f in range(F)])
+            want = [oracle.oracle_ssim(a[f], b[f], want_map=True) for f in range(F)]
+            dA, dB = _dev(a), _dev(b)
+            dMap = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+            dSsim = torch.empty(F, dtype=torch.float32, device="cuda")
+            for wave, rows in ((-1, 0), (64, 0), (200, 0), (-1, 200), (-1, 5000), (100, 1), (0, 0)):
+                lib.ssim_cuda_set_tuning(wave, rows)
+                dMap.zero_(); dSsim.zero_()
+                api.compute_device(0, None, W, H, 0, H, F, dA.data_ptr(), W, W * H, dB.data_ptr(), W, W * H, dMap.data_ptr(), W, W * H, None, dSsim.data_ptr())
+                torch.cuda.synchronize()
+                for f in range(F):
+                    assert abs(float(dSsim[f]) - float(want[f][0])) <= GLOBAL_TOL, (W, H, F, wave, rows, f)
+                    assert np.abs(dMap[f].cpu().numpy() - want[f][2]).max() <= PIXEL_TOL, (W, H, F, wave, rows, f)
     finally:
         lib.ssim_cuda_set_tuning(0, 0)
 

@@ -21,4 +21,4 @@ def run(F, reps):
     e1.record(st); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     print("%2d x 4K: %8.1f us per call = %8.0f Mpix/s  ssim %.6f" % (F, us, F * W * H / us, float(val[0])))
-run(64, 10); run(1, 50); run(64, 10)
+run(16, 20); run(64, 10); run(16, 20); run(128, 5)
