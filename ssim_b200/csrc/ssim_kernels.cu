@@ -431,7 +431,7 @@ __device__ __forceinline__ void frame_arrive(const FusedParams& p, const Exchang
     // fixed order (slot order, lanes strided, then the shuffle tree): deterministic.  The loads are issued in batches so
     // that their L2 latencies overlap (one dependent load per add cost 13 us for the 1184 partials of a single frame).
     double acc = 0.0;
-    constexpr int kBatch = 8;
+    constexpr int kBatch = 40;                          // one batch covers the 8 x 148 partials of a single frame
     for (uint32_t s0 = sLo + lane; s0 <= sHi; s0 += 32 * kBatch) {
         double v[kBatch];
         #pragma unroll

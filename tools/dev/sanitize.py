@@ -1,0 +1,17 @@
+"""Dev: a few small launches of every kernel variant for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import sys
+sys.path.insert(0, '/root/repo')
+import numpy as np
+from ssim_b200 import api
+from ssim_b200.synth import synth_pair
+lib = api.cuda_lib()
+for (w, h) in ((333, 141), (68, 97), (640, 360), (1284, 31)):
+    a, b = synth_pair(w, h, 2)
+    print(w, h, api.compute_ssim(a, b, want_map=True)[0], api.compute_ssim(a, b)[0],
+          api.compute_u16(a.astype(np.uint16) * 257, b.astype(np.uint16) * 257, want_map=True)[0])
+a = np.stack([synth_pair(200, 90, 1)[0]] * 3, axis=-1).copy(); b = np.stack([synth_pair(200, 90, 1)[1]] * 3, axis=-1).copy()
+print("channels", api.compute_channels(a, b, want_map=True)[0])
+lib.ssim_cuda_set_tuning(64, 0)          # waves of 4-pair CTAs on a small input
+a, b = synth_pair(640, 720, 5)
+print("waves", api.compute_ssim(a, b, want_map=True)[0])
+lib.ssim_cuda_set_tuning(0, 0)
