@@ -171,12 +171,11 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
                          uint32_t width, uint32_t rows, uint32_t y0, uint32_t frame, uint64_t seed);
 
 /*
- * Tuning knobs of the work partition, for experiments/bench only (0 = automatic for either): waveRows is the share of rows
- * a warp pair gets when a large input is run as many CTAs in waves (default 540; -1 = always a single wave of resident
- * CTAs), minSlotRows is the smallest share (incl. the 10 start-up rows per column) a warp pair is given before fewer pairs
- * are used.  Process-wide.
+ * Tuning knobs of the persistent kernel's work partition, for experiments/bench only (0 = automatic for either):
+ * maxPairsPerSm caps the warp pairs per SM the work is spread over (1..8), minSlotRows is the smallest share of rows (incl.
+ * the 10 start-up rows per column) a warp pair is given before fewer pairs are used.  Process-wide.
  */
-void ssim_cuda_set_tuning(int waveRows, int minSlotRows);
+void ssim_cuda_set_tuning(int maxPairsPerSm, int minSlotRows);
 
 /*
  * Development aid: while dTimes (device memory, 32 x 64-bit words per warp pair of the persistent grid, i.e. at least

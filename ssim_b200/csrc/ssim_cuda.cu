@@ -38,7 +38,7 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int  g_lastLaunches = 0;
 std::atomic<int> g_minSlotRows{0};       // tuning knobs (0 = automatic), see ssim_cuda_set_tuning()
-std::atomic<int> g_waveRows{0};
+std::atomic<int> g_maxPairsPerSm{0};
 std::atomic<unsigned long long*> g_dbgTimes{nullptr};   // development aid, see ssim_cuda_debug_slot_times()
 
 int fail(int code, const char* fmt, ...)
@@ -166,7 +166,7 @@ int make_plane_map(CUtensorMap* tm, const uint8_t* base, uint32_t width, uint32_
 
 // Descriptor cache: a video sweep or a pipelined host call presents the same (pointer, geometry) again and again (frame
 // rings, the context's own scratch planes), and encoding a tensor map costs a driver call of a few microseconds -- as much
-// as the kernel launch itself.  Per thread (no lock), 16 entries, round-robin replacement.  A descriptor only holds the
+// as the kernel launch itself.  Per thread (no lock), 512 entries, direct-mapped.  A descriptor only holds the
 // address and the geometry, so a hit on a pointer that was freed and re-allocated with the same geometry is still right.
 struct MapKey {
     const uint8_t* base; size_t pitch, frameStride; uint32_t width, rows, frames; int elemBytes;
@@ -177,25 +177,28 @@ struct MapKey {
     }
 };
 struct MapCache {
-    static const int kEntries = 16;
+    static const int kEntries = 512;          // direct-mapped by a hash of the key: a ring of 64 4K frames is 128 descriptors
     MapKey key[kEntries];
     alignas(64) CUtensorMap tm[kEntries];
-    int used = 0, next = 0;
+    MapCache() { memset(key, 0, sizeof(key)); }
 };
-thread_local MapCache g_mapCache;
+thread_local std::unique_ptr<MapCache> g_mapCache;
 
 int get_plane_map(const CUtensorMap** out, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
                   size_t frameStride, int elemBytes)
 {
-    MapCache& mc = g_mapCache;
+    if (!g_mapCache) g_mapCache.reset(new MapCache());
+    MapCache& mc = *g_mapCache;
     const MapKey k = {base, pitch, frames > 1 ? frameStride : 0, width, rows, frames, elemBytes};
-    for (int i = 0; i < mc.used; ++i)
-        if (mc.key[i] == k) { *out = &mc.tm[i]; return 0; }
-    const int slot = mc.used < MapCache::kEntries ? mc.used : mc.next;
+    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+    h ^= ((uint64_t)width << 32 | rows) * 0xC2B2AE3D27D4EB4Full;
+    h ^= (uint64_t)pitch * 0x165667B19E3779F9ull + frames + (uint64_t)elemBytes * 131;
+    const int slot = (int)((h >> 40) % MapCache::kEntries);
+    if (mc.key[slot] == k && k.base != nullptr) { *out = &mc.tm[slot]; return 0; }
+    mc.key[slot].base = nullptr;
     int rc = make_plane_map(&mc.tm[slot], base, width, rows, frames, pitch, frameStride, elemBytes);
-    if (rc) { if (slot < mc.used) mc.key[slot].base = nullptr; return rc; }
+    if (rc) return rc;
     mc.key[slot] = k;
-    if (mc.used < MapCache::kEntries) ++mc.used; else mc.next = (mc.next + 1) % MapCache::kEntries;
     *out = &mc.tm[slot];
     return 0;
 }
@@ -232,7 +235,7 @@ struct Workspace {             // reduction workspace of one stream, see get_wor
 struct Context {
     int device = -1;
     int numSMs = 0;
-    int pairsPerSm = ssimk::kPairsFair;       // warp pairs resident per SM
+    int pairsPerSm = ssimk::kPairsPerCta;     // warp pairs resident per SM
     cudaStream_t stream = nullptr;            // stream of the blocking host-pointer path (compute)
     cudaStream_t streamIn = nullptr;          // pipelined host path: H2D copies
     cudaStream_t streamOut = nullptr;         // pipelined host path: D2H copies
@@ -300,7 +303,7 @@ int create_context(int device, Context** out)
     c->chunkSumsHost.pinnedHost = true;
     int regsMap = 0, regsNoMap = 0, pairs = 0;
     CU_TRY(ssimk::fused_kernel_attributes(&regsMap, &regsNoMap, &pairs));
-    if (pairs < ssimk::kPairsFair) return fail(EIO, "the fused kernel does not fit this device (%d warp pairs per SM)", pairs);
+    if (pairs < ssimk::kPairsPerCta) return fail(EIO, "the fused kernel does not fit this device (%d warp pairs per SM)", pairs);
     c->pairsPerSm = pairs;
     *out = c.release();
     return 0;
@@ -365,16 +368,13 @@ int acquire_host_context(Context** c, std::unique_lock<std::mutex>* lock)
 // columns evenly.  The only choices left to the host are how many CTAs per SM to use and how thin the work may be spread
 // (a slot pays 10 start-up rows, so tiny inputs use fewer slots).
 const uint32_t kDefaultMinSlotRows = 12;
-const int kDefaultWaveRows = 540;         // share of a warp pair in waves mode (about the 540-row segments r1 measured best)
 
-bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, bool singleWave, ssimk::SlotPlan* plan)
+bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, ssimk::SlotPlan* plan)
 {
     const int minRows = g_minSlotRows.load(std::memory_order_relaxed);
-    int waveRows = g_waveRows.load(std::memory_order_relaxed);
-    if (waveRows == 0) waveRows = kDefaultWaveRows;
-    if (waveRows > 0 && waveRows < 64) waveRows = 64;
-    return ssimk::plan_slots((uint32_t)(c->numSMs * c->pairsPerSm), width, outRows, frames,
-                             minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan, singleWave || waveRows < 0 ? 0u : (uint32_t)waveRows);
+    int pairs = g_maxPairsPerSm.load(std::memory_order_relaxed);
+    if (pairs <= 0 || pairs > c->pairsPerSm) pairs = c->pairsPerSm;
+    return ssimk::plan_slots((uint32_t)(c->numSMs * pairs), width, outRows, frames, minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan);
 }
 
 // Reduction workspace of a stream: per-frame arrival counters (zero between launches: the kernel resets them), then
@@ -429,8 +429,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (dMap && mapStep != 1 && elemBytes != 1) return fail(EINVAL, "maps with a pixel step are supported for 8-bit images only");
 
     ssimk::SlotPlan plan;
-    // strips exchanged with peers spin on the other GPUs' kernels: keep those launches in a single wave
-    if (!plan_for(c, width, outRows, frames, xchg != nullptr, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
+    if (!plan_for(c, width, outRows, frames, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
 
     WorkspaceView ws;
     int rc = get_workspace(c, stream, frames, (size_t)plan.slots * plan.entries, &ws);
@@ -441,7 +440,6 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
 
     ssimk::FusedParams p;
     memset(&p, 0, sizeof(p));
-    p.pairsPerCta = (int)plan.pairsPerCta;
     p.u16 = elemBytes == 2;
     p.a = dA; p.b = dB;
     p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
@@ -1224,9 +1222,9 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
 
 void ssim_cuda_debug_slot_times(unsigned long long* dTimes) { g_dbgTimes.store(dTimes, std::memory_order_relaxed); }
 
-void ssim_cuda_set_tuning(int waveRows, int minSlotRows)
+void ssim_cuda_set_tuning(int maxPairsPerSm, int minSlotRows)
 {
-    g_waveRows.store(waveRows, std::memory_order_relaxed);
+    g_maxPairsPerSm.store(maxPairsPerSm > 0 ? maxPairsPerSm : 0, std::memory_order_relaxed);
     g_minSlotRows.store(minSlotRows > 0 ? minSlotRows : 0, std::memory_order_relaxed);
 }
 

@@ -666,8 +666,8 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
     }
 }
 
-template <int kMap, bool kU16, int kPairsPerCta>
-__global__ void __launch_bounds__(2 * kPairsPerCta * 32, 8 / kPairsPerCta)
+template <int kMap, bool kU16>
+__global__ void __launch_bounds__(kCtaThreads, 1)
 ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ FusedParams p, const __grid_constant__ ExchangeParams x)
 {
@@ -806,58 +806,38 @@ __global__ void synth_fill_kernel(uint8_t* __restrict__ dA, long long pitchA, ui
 
 // ------------------------------------------------------------------------------------------------ launchers
 // cudaFuncSetAttribute is per DEVICE: called from every device context's initialisation (current device = that device)
-template <int kMap, bool kU16, int kPairs>
+template <int kMap, bool kU16>
 static cudaError_t set_smem_attr_one()
 {
-    return cudaFuncSetAttribute(ssim_fused_kernel<kMap, kU16, kPairs>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairs * PixGeo<kU16>::kPairSmemBytes);
-}
-template <int kPairs>
-static cudaError_t set_smem_attr_shape()
-{
-    cudaError_t e = set_smem_attr_one<0, false, kPairs>();
-    if (e == cudaSuccess) e = set_smem_attr_one<1, false, kPairs>();
-    if (e == cudaSuccess) e = set_smem_attr_one<2, false, kPairs>();
-    if (e == cudaSuccess) e = set_smem_attr_one<0, true, kPairs>();
-    if (e == cudaSuccess) e = set_smem_attr_one<1, true, kPairs>();
-    return e;
+    return cudaFuncSetAttribute(ssim_fused_kernel<kMap, kU16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PixGeo<kU16>::kCtaSmemBytes);
 }
 static cudaError_t set_smem_attr()
 {
-    cudaError_t e = set_smem_attr_shape<kPairsFair>();
-    if (e == cudaSuccess) e = set_smem_attr_shape<kPairsWave>();
+    cudaError_t e = set_smem_attr_one<0, false>();
+    if (e == cudaSuccess) e = set_smem_attr_one<1, false>();
+    if (e == cudaSuccess) e = set_smem_attr_one<2, false>();
+    if (e == cudaSuccess) e = set_smem_attr_one<0, true>();
+    if (e == cudaSuccess) e = set_smem_attr_one<1, true>();
     return e;
-}
-
-template <int kMap, bool kU16, int kPairs>
-static void launch_one(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams& x)
-{
-    const unsigned ctas = (p.geo.slots + kPairs - 1) / kPairs;
-    ssim_fused_kernel<kMap, kU16, kPairs><<<ctas, 2 * kPairs * 32, kPairs * PixGeo<kU16>::kPairSmemBytes, stream>>>(tmA, tmB, p, x);
-}
-template <int kPairs>
-static cudaError_t launch_shape(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams& x)
-{
-    const int mapKind = !p.map ? 0 : p.mapStep == 1 ? 1 : 2;
-    if (p.u16) {
-        if (mapKind == 2) return cudaErrorInvalidValue;              // 16-bit pixels: dense maps only
-        if (mapKind) launch_one<1, true, kPairs>(stream, tmA, tmB, p, x);
-        else         launch_one<0, true, kPairs>(stream, tmA, tmB, p, x);
-    } else {
-        if (mapKind == 2)      launch_one<2, false, kPairs>(stream, tmA, tmB, p, x);
-        else if (mapKind == 1) launch_one<1, false, kPairs>(stream, tmA, tmB, p, x);
-        else                   launch_one<0, false, kPairs>(stream, tmA, tmB, p, x);
-    }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams* xchg)
 {
-    if (p.geo.slots == 0) return cudaErrorInvalidValue;
+    const unsigned ctas = (p.geo.slots + kPairsPerCta - 1) / kPairsPerCta;
+    if (ctas == 0) return cudaErrorInvalidValue;
     ExchangeParams none;
     if (!xchg) { memset(&none, 0, sizeof(none)); xchg = &none; }
-    if (p.pairsPerCta == kPairsWave) return launch_shape<kPairsWave>(stream, tmA, tmB, p, *xchg);
-    if (p.pairsPerCta == kPairsFair) return launch_shape<kPairsFair>(stream, tmA, tmB, p, *xchg);
-    return cudaErrorInvalidValue;
+    const int mapKind = !p.map ? 0 : p.mapStep == 1 ? 1 : 2;
+    if (p.u16) {
+        if (mapKind == 2) return cudaErrorInvalidValue;              // 16-bit pixels: dense maps only
+        if (mapKind) ssim_fused_kernel<1, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        else         ssim_fused_kernel<0, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+    } else {
+        if (mapKind == 2)      ssim_fused_kernel<2, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        else if (mapKind == 1) ssim_fused_kernel<1, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+        else                   ssim_fused_kernel<0, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* pairsPerSm)
@@ -865,19 +845,16 @@ cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* pairsPerS
     cudaError_t e = set_smem_attr();
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<1, false, kPairsFair>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<1, false>)) != cudaSuccess) return e;
     if (regsMap) *regsMap = fa.numRegs;
-    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<0, false, kPairsFair>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, ssim_fused_kernel<0, false>)) != cudaSuccess) return e;
     if (regsNoMap) *regsNoMap = fa.numRegs;
-    // warp pairs resident per SM: the smaller of the two shapes' occupancies (8 for both by construction)
-    int nFair = 0, nWave = 0, n16 = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nFair, ssim_fused_kernel<1, false, kPairsFair>, 2 * kPairsFair * 32, kPairsFair * PixGeo<false>::kPairSmemBytes);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nWave, ssim_fused_kernel<1, false, kPairsWave>, 2 * kPairsWave * 32, kPairsWave * PixGeo<false>::kPairSmemBytes);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<1, true, kPairsFair>, 2 * kPairsFair * 32, kPairsFair * PixGeo<true>::kPairSmemBytes);
-    int pairs = nFair * kPairsFair;
-    if (nWave * kPairsWave < pairs) pairs = nWave * kPairsWave;
-    if (n16 * kPairsFair < pairs) pairs = n16 * kPairsFair;
-    if (pairsPerSm) *pairsPerSm = pairs;
+    // warp pairs resident per SM (one CTA of kPairsPerCta for every variant, by construction)
+    int n = 0, n16 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ssim_fused_kernel<1, false>, kCtaThreads, PixGeo<false>::kCtaSmemBytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n16, ssim_fused_kernel<1, true>, kCtaThreads, PixGeo<true>::kCtaSmemBytes);
+    if (n16 < n) n = n16;
+    if (pairsPerSm) *pairsPerSm = n * kPairsPerCta;
     return e;
 }
 

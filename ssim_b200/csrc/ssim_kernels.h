@@ -17,17 +17,16 @@ constexpr int kBoxLeft     = 16;   // band column 0 sits at byte 16 of a box row
                                    // (tools/dev/tma_probe.cu)
 constexpr int kLoadRows    = 8;    // rows per TMA box (= one horizontal-pass block)
 constexpr int kStages      = 2;    // TMA stages per warp pair
-// Two CTA shapes, 16 warps per SM either way (measured, tools/dev/slot_times.py and profiles/r02_cta_shapes.txt):
-//   * two CTAs of 4 warp pairs (256 threads): the warp schedulers serve the CTA that arrived first on an SM with priority --
-//     its pairs run 2.2x as fast as those of the second CTA (1.8 vs 3.9 us per 8 rows on 4K batches) -- and the SM as a whole
-//     gets 7% MORE done than with evenly served warps (3.26 vs 3.03 blocks/us): the favoured pairs hardly ever wait for an
-//     issue slot, the others fill the gaps.  Good for throughput, fatal for a static partition (the second CTAs finish 45%
-//     later), so this shape is used with MANY more CTAs than fit at once: each CTA does a modest share and the hardware's
-//     block scheduler hands the next CTA to whichever SM has room -- dynamic load balancing for free.
-//   * one CTA of 8 warp pairs (512 threads): the warps of one CTA are served evenly (all 8 pairs finish within 1%), which is
-//     what a single wave needs: small and medium inputs, where every pair gets exactly one equal share.
-constexpr int kPairsWave   = 4;    // warp pairs per CTA in the many-CTAs ("waves") mode
-constexpr int kPairsFair   = 8;    // warp pairs per CTA in the single-wave mode
+// ONE CTA of 8 warp pairs (512 threads) per SM, not two of 4.  Measured (tools/dev/slot_times.py, profiles/r02_cta_shapes.txt):
+// with two resident CTAs the warp schedulers serve the CTA that arrived first on an SM with priority -- its pairs run 2.2x
+// as fast as those of the second CTA (1.8 vs 3.9 us per 8 rows on 4K batches) -- so a static, equal partition ends 45% late
+// on the second CTAs, and which CTA of a grid arrives first on an SM is not a function of blockIdx.  The warps of ONE CTA
+// are served evenly: all 8 pairs of every CTA finish within 1% of each other.  (The unfair arrangement gets ~4% more
+// instructions per cycle out of an SM while both CTAs run; cutting large inputs into many small CTAs so that the hardware
+// block scheduler balances them -- what round 1 did -- measured 1% better than the single even wave on 64 x 4K and 7%
+// worse on 16 x 4K, and was dropped.)
+constexpr int kPairsPerCta = 8;    // warp pairs per CTA: each is one producer warp and one consumer warp
+constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 512: warps 0-7 producers (TMA + horizontal pass), 8-15 consumers
 constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
 constexpr int kConsumerRegs = 160;
 constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partner warp's mbarrier
@@ -53,12 +52,13 @@ template <bool kU16> struct PixGeo {
     static constexpr int kBoxLeftElems  = kBoxLeft / kPixBytes;             // 16 / 8
     static constexpr int kImgStageBytes = kBoxBytes * kLoadRows;            // 768 / 1280
     static constexpr int kStageBytes    = 2 * kImgStageBytes;               // 1536 / 2560
-    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 26368 / 28416: 8 pairs per SM
+    static constexpr int kPairSmemBytes = (kStages * kStageBytes + kRingBytes + 127) / 128 * 128;   // 26368 / 28416
+    static constexpr int kCtaSmemBytes  = kPairsPerCta * kPairSmemBytes;    // 210944 / 227328: one CTA per SM
 };
 
 // ---- work partition --------------------------------------------------------------------------------------------------
-// `slots` warp pairs share the work evenly and statically (single-wave mode: at most 8 x numSMs of them, all resident at
-// once; waves mode: many more, served by the hardware's block scheduler as CTAs retire).  Pairs work in TEAMS of `group` (1..8) pairs with consecutive slot numbers: a team walks
+// The kernel is persistent: `slots` warp pairs (at most kPairsPerCta x numSMs, all resident at once) share the work evenly
+// and statically.  Pairs work in TEAMS of `group` (1..8) pairs with consecutive slot numbers: a team walks
 // down `group` ADJACENT 64-pixel bands side by side, member m taking band group*k + m, all members over the same rows.
 // (Neighbouring bands share the 16-byte margins of their TMA boxes, i.e. sectors and DRAM atoms; pairs that reach the same
 // rows at unrelated times each fetch them from DRAM again.  Measured with every pair on its own: 4.0x the algorithmic DRAM
@@ -77,7 +77,6 @@ constexpr int kPad = 2 * kHalo;
 constexpr int kDbgWords = 32;
 
 struct SlotPlan {
-    uint32_t pairsPerCta;    // kPairsFair (single wave, one CTA per SM) or kPairsWave (many CTAs, two per SM at a time)
     uint32_t slots;          // warp pairs that get work = teams * group
     uint32_t group;          // pairs per team = adjacent bands walked side by side
     uint32_t shareQ, shareR; // units per team: team j owns shareQ + (j < shareR) units
@@ -87,11 +86,8 @@ struct SlotPlan {
 
 // Pure host logic (unit-tested on the CPU: tests/clients/plan_check.cpp).  maxSlots: warp pairs resident at once (8 per SM).
 // minUnits: do not spread the work thinner than this many units per slot (tiny images would otherwise pay 10 start-up rows
-// for a handful of output rows per slot).  waveUnits: when every resident pair would get at least 3 x waveUnits units the
-// work is cut into shares of about waveUnits units instead and run in waves of 4-pair CTAs (0 = never); the share is
-// nudged so that the last wave of CTAs is nearly full.
-inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint32_t frames, uint32_t minUnits, SlotPlan* plan,
-                       uint32_t waveUnits = 0)
+// for a handful of output rows per slot).
+inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint32_t frames, uint32_t minUnits, SlotPlan* plan)
 {
     const unsigned long long bands = ((unsigned long long)width + kBandW - 1) / kBandW;
     const unsigned long long colUnits = (unsigned long long)outRows + kPad;
@@ -113,24 +109,6 @@ inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint
     unsigned long long teams = units / minUnits;
     if (teams > maxSlots / group) teams = maxSlots / group;
     if (teams < 1) teams = 1;
-    plan->pairsPerCta = kPairsFair;
-    if (waveUnits > 0 && units / teams >= 3ull * waveUnits) {
-        // waves mode: among the team counts that give shares of 0.75 .. 1.5 x waveUnits pick the one that wastes the least of
-        // the last wave (resident CTAs = maxSlots / kPairsWave) -- cost = waves x (share + start-up), a partly filled last
-        // wave counting in proportion
-        const unsigned long long resident = maxSlots / kPairsWave;
-        unsigned long long bestTeams = units / waveUnits;
-        double best = 1e300;
-        for (unsigned long long t = units / (waveUnits + waveUnits / 2) + 1; t <= units / (waveUnits - waveUnits / 4); ++t) {
-            const unsigned long long ctas = (t * group + kPairsWave - 1) / kPairsWave;
-            const double waves = (double)(ctas / resident) + ((ctas % resident) ? 0.35 + 0.65 * (double)(ctas % resident) / (double)resident : 0.0);
-            const double cost = waves * ((double)(units / t) + kPad + 12);
-            if (cost < best) { best = cost; bestTeams = t; }
-            if (t - units / (waveUnits + waveUnits / 2) > 4096) break;      // plenty of candidates seen
-        }
-        teams = bestTeams;
-        plan->pairsPerCta = kPairsWave;
-    }
     plan->slots = (uint32_t)(teams * group);
     plan->group = (uint32_t)group;
     plan->shareQ = (uint32_t)(units / teams);
@@ -211,7 +189,6 @@ SSIMK_HD bool cursor_next(PieceCursor& c, const SlotGeo& g, Piece& pc)
 }
 
 struct FusedParams {
-    int pairsPerCta;         // CTA shape: kPairsFair or kPairsWave (SlotPlan::pairsPerCta)
     int u16;                 // 0: 8-bit pixels, 1: 16-bit pixels (pitches and frame strides stay in BYTES)
     const uint8_t* a;        // raw planes (used only to fetch the per-piece centring pixel)
     const uint8_t* b;
@@ -279,7 +256,7 @@ struct ExchangeParams {
 };
 
 // ONE launch per call: TMA loads, both filter passes, the formula, the map, the per-frame reduction and (xchg != NULL) the
-// cross-GPU sum.  The grid is ceil(p.geo.slots / p.pairsPerCta) CTAs.
+// cross-GPU sum.  The grid is ceil(p.geo.slots / kPairsPerCta) CTAs, all resident.
 cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const FusedParams& p, const ExchangeParams* xchg);
 // per-device preparation (sets the dynamic shared-memory limit on the CURRENT device) + kernel facts
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* pairsPerSm);

@@ -14,17 +14,14 @@ static void expect(bool ok, const char* what, uint32_t w, uint32_t h, uint32_t f
     if (!ok) ++fails;
 }
 
-static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_t minUnits, uint32_t waveUnits = 0)
+static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_t minUnits)
 {
     ssimk::SlotPlan plan;
-    if (!ssimk::plan_slots(maxSlots, w, h, f, minUnits, &plan, waveUnits)) { expect(false, "plan_slots refused", w, h, f, maxSlots); return; }
+    if (!ssimk::plan_slots(maxSlots, w, h, f, minUnits, &plan)) { expect(false, "plan_slots refused", w, h, f, maxSlots); return; }
     const ssimk::SlotGeo g = ssimk::make_slot_geo(plan, w);
     const uint32_t bands = (w + 63) / 64;
     const uint64_t cols = (uint64_t)bands * f;
-    expect(plan.slots >= 1 && (plan.slots <= maxSlots || plan.pairsPerCta == ssimk::kPairsWave), "slot count in range", w, h, f, plan.slots);
-    expect(plan.pairsPerCta == ssimk::kPairsFair || (plan.pairsPerCta == ssimk::kPairsWave && waveUnits > 0), "CTA shape", w, h, f, plan.slots);
-    if (plan.pairsPerCta == ssimk::kPairsWave)
-        expect(plan.shareQ * 4 >= waveUnits * 3 - 4 && plan.shareQ * 2 <= waveUnits * 3 + 2 && plan.slots > maxSlots, "waves mode: shares of 0.75 .. 1.5 waveUnits, more slots than fit at once", w, h, f, plan.slots);
+    expect(plan.slots >= 1 && plan.slots <= maxSlots, "slot count in range", w, h, f, plan.slots);
     expect(plan.group >= 1 && plan.group <= 8 && plan.slots % plan.group == 0, "whole teams of 1..8 pairs", w, h, f, plan.slots);
     const uint32_t teams = plan.slots / plan.group;
     expect((uint64_t)teams * plan.shareQ + plan.shareR == (uint64_t)g.groupsPerFrame * f * (h + 10), "shares add up to all units", w, h, f, plan.slots);
@@ -70,22 +67,16 @@ int main()
     for (uint32_t w : widths) for (uint32_t h : heights) for (uint32_t f : frames) {
         if ((uint64_t)((w + 63) / 64) * f * (h + 10) > 40000000ull) continue;     // keep the check fast
         check(slots, w, h, f, 24);
-        check(slots, w, h, f, 24, 540);
         check(slots / 2, w, h, f, 1);
         check(7, w, h, f, 100);
     }
     check(slots, 1920, 1080, 4096, 24);
-    check(slots, 1920, 1080, 4096, 24, 540);
-    check(64, 3840, 2160, 8, 24, 100);
     check(slots, 64, 64, 4096, 24);
     check(1, 3840, 2160, 2, 24);
     // the documented plans
     ssimk::SlotPlan p;
     ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p);   expect(p.group == 6 && p.slots == 1182 && p.shareQ == 110 && p.entries == 1, "one 4K pair: 197 teams of 6 bands, 110-111 units each", 3840, 2160, 1, p.slots);
     ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p);  expect(p.group == 6 && p.slots == 1182 && p.shareQ == 7049, "64 x 4K", 3840, 2160, 64, p.slots);
-    ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p, 540); expect(p.pairsPerCta == 4 && p.group == 6 && p.shareQ >= 405 && p.shareQ <= 810, "64 x 4K in waves of 4-pair CTAs", 3840, 2160, 64, p.slots);
-    std::printf("64 x 4K waves plan: %u slots, %u units per team share, %.2f waves of CTAs\n", p.slots, p.shareQ, (p.slots + 3) / 4 / 296.0);
-    ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p, 540);  expect(p.pairsPerCta == 8, "one 4K pair stays a single wave", 3840, 2160, 1, p.slots);
     ssimk::plan_slots(slots, 16384, 2058, 1, 24, &p);  expect(p.group == 8 && p.slots == 1184, "a 16384-wide strip: one team of 8 bands per CTA", 16384, 2058, 1, p.slots);
     ssimk::plan_slots(slots, 1920, 1080, 1, 24, &p);   expect(p.group == 6 && p.slots == 1182, "1080p: 5 groups of 6 bands", 1920, 1080, 1, p.slots);
     ssimk::plan_slots(slots, 333, 141, 1, 24, &p);     expect(p.group == 6 && p.slots == 36, "small image: fewer slots", 333, 141, 1, p.slots);

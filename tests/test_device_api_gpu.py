@@ -109,8 +109,8 @@ def test_many_frames_are_reduced_per_frame(shape):
 
 
 def test_tuning_knobs_do_not_change_results():
-    """ssim_cuda_set_tuning: any partition of the work (single wave of 8-pair CTAs or waves of 4-pair CTAs, any share size)
-    gives the same map values up to the per-piece centring (different pieces, same math)"""
+    """ssim_cuda_set_tuning: any partition of the work (fewer warp pairs per SM, any minimum share) gives the same map values up
+    to the per-piece centring (different pieces, same math)"""
     lib = api.cuda_lib()
     try:
         for (W, H, F) in ((640, 360, 1), (1920, 1080, 3)):
@@ -120,7 +120,7 @@ def test_tuning_knobs_do_not_change_results():
             dA, dB = _dev(a), _dev(b)
             dMap = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
             dSsim = torch.empty(F, dtype=torch.float32, device="cuda")
-            for wave, rows in ((-1, 0), (64, 0), (200, 0), (-1, 200), (-1, 5000), (100, 1), (0, 0)):
+            for wave, rows in ((1, 0), (3, 0), (8, 200), (5, 5000), (2, 1), (0, 0)):
                 lib.ssim_cuda_set_tuning(wave, rows)
                 dMap.zero_(); dSsim.zero_()
                 api.compute_device(0, None, W, H, 0, H, F, dA.data_ptr(), W, W * H, dB.data_ptr(), W, W * H, dMap.data_ptr(), W, W * H, None, dSsim.data_ptr())
