@@ -12,7 +12,7 @@ OBJ     := build/obj
 
 BIN     := ssim_b200/bin
 
-all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so $(BIN)/rmgr-ssim
+all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so $(BIN)/rmgr-ssim $(BIN)/latency_client
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/ssim_kernels.h $(CSRC)/synth.h include/ssim_cuda.h
 	@mkdir -p $(OBJ)
@@ -33,6 +33,11 @@ $(LIB)/librmgr-ssim.so: $(OBJ)/rmgr_api.o $(LIB)/libssim_cuda.so
 $(BIN)/rmgr-ssim: $(CSRC)/ssim_cli.cpp $(LIB)/librmgr-ssim.so $(LIB)/libssim_cuda.so
 	@mkdir -p $(BIN)
 	$(HOSTCXX) -O2 -std=c++17 -Iinclude -o $@ $(CSRC)/ssim_cli.cpp -L$(LIB) -lrmgr-ssim -lssim_cuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
+
+# latency_client: what one device-pointer call costs a C++ caller (used by bench.py for the single-pair latency)
+$(BIN)/latency_client: $(CSRC)/latency_client.cpp $(LIB)/libssim_cuda.so
+	@mkdir -p $(BIN)
+	$(HOSTCXX) -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include -o $@ $(CSRC)/latency_client.cpp -L$(LIB) -lssim_cuda -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../lib' -Wl,-rpath,/usr/local/cuda/lib64
 
 oracle:
 	$(MAKE) -C oracle

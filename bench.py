@@ -138,6 +138,20 @@ def pcie_probe(torch, dist, world, dev, seconds=0.15):
     return n * reps / e[0].elapsed_time(e[1]) / 1e6, n * reps / e[2].elapsed_time(e[3]) / 1e6
 
 
+def c_client(w, h, with_map, reps=50):
+    """The same latency measured by a compiled C++ caller (ssim_b200/bin/latency_client, csrc/latency_client.cpp): no Python in
+    the timed path.  Returns its JSON, or a note when the binary is not built."""
+    import subprocess
+    exe = os.path.join(ROOT, "ssim_b200", "bin", "latency_client")
+    if not os.path.exists(exe):
+        return {"unavailable": "ssim_b200/bin/latency_client not built"}
+    try:
+        r = subprocess.run([exe, str(w), str(h), str(with_map), str(reps)], capture_output=True, text=True, timeout=120)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:                                 # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def config(args, n):
     return {"workload": "3840x2160 8-bit grayscale pairs with per-pixel map (BASELINE.json configs[2]), %d pairs per GPU per step" % args.frames,
             "frames_per_gpu_per_step": args.frames, "width": W, "height": H,
@@ -352,6 +366,8 @@ def run_extras(args, api, torch, dist, local, rank, world, stream, barrier):
     out["1080p_pair_no_map"]["e2e_us_per_pair"] = round(dt * 1e6, 1)
     out["1080p_pair_no_map"]["e2e_mpix_per_s"] = round(w * h / dt / 1e6, 1)
     out["1080p_pair_no_map"]["e2e_ssim"] = float(e2e_val)
+    if rank == 0:
+        out["1080p_pair_no_map"]["c_client"] = c_client(1920, 1080, 0)
 
     # configs[3]: ONE 16384x16384 pair split into row strips with 5-row halos across the ranks, map strips written,
     # double partial sums all-reduced with NCCL inside the timed region
@@ -590,12 +606,14 @@ def run_ours(args):
 
     # ---- one 4K pair per launch (latency view; BASELINE.md: <= 42.7 us is the 60% target)
     single = []
+    ptrs = [(dA[f].data_ptr(), dB[f].data_ptr(), dMap[f].data_ptr()) for f in range(F)]      # no tensor indexing inside the timed calls
+    pS, pV = dSums.data_ptr(), dSsim.data_ptr()
     for i in range(3 + 20):
-        f = i % F
+        pa, pb, pm = ptrs[i % F]
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
         s0.record(stream)
-        api.compute_device(local, sh, W, H, 0, H, 1, dA[f].data_ptr(), W, npx, dB[f].data_ptr(), W, npx, dMap[f].data_ptr(), W, npx,
-                           dSums.data_ptr(), dSsim.data_ptr())
+        api.compute_device(local, sh, W, H, 0, H, 1, pa, W, npx, pb, W, npx, pm, W, npx, pS, pV)
         s1.record(stream)
         torch.cuda.synchronize()
         if i >= 3:
@@ -605,9 +623,8 @@ def run_ours(args):
     q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     q0.record(stream)
     for i in range(40):
-        f = i % F
-        api.compute_device(local, sh, W, H, 0, H, 1, dA[f].data_ptr(), W, npx, dB[f].data_ptr(), W, npx, dMap[f].data_ptr(), W, npx,
-                           dSums.data_ptr(), dSsim.data_ptr())
+        pa, pb, pm = ptrs[i % F]
+        api.compute_device(local, sh, W, H, 0, H, 1, pa, W, npx, pb, W, npx, pm, W, npx, pS, pV)
     q1.record(stream)
     torch.cuda.synchronize()
     single_queued_us = q0.elapsed_time(q1) * 1e3 / 40
@@ -719,7 +736,8 @@ def run_ours(args):
                                "mpix_per_s_at_median": round(npx / statistics.median(single), 1),
                                "queued_us_per_pair": round(single_queued_us, 2),
                                "note": "one 4K pair with map per call = one launch: median/min = events around a single call on an idle stream "
-                                       "(host-side launch cost included), queued = 40 calls (rotating frames) queued back to back"},
+                                       "(host-side launch cost of the Python/ctypes caller included), queued = 40 calls (rotating frames) queued back to back",
+                               "c_client": c_client(3840, 2160, 1)},
             "ssim_frame0": ssim_first, "ssim_e2e_last": float(e2e_last)}
     if extras is not None:
         line["other_configs"] = extras

@@ -539,12 +539,18 @@ struct GeneralJob {
     float* map = nullptr;
     ptrdiff_t mapStep = 0, mapStride = 0;
     bool cpuScatter = false;
+    // the map's way back to the caller, when it is not written in place: enqueued by return_map()
+    float* dMap = nullptr;
+    size_t dMapPitch = 0;
+    bool mapDirect = false, mapOnDevice = false;
 };
+
+int return_map(GeneralJob* job);
 
 int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, uint32_t outRows, const uint8_t* a, ptrdiff_t stepA,
                     ptrdiff_t strideA, const uint8_t* b, ptrdiff_t stepB, ptrdiff_t strideB, float* map, ptrdiff_t mapStep,
                     ptrdiff_t mapStride, bool wantSsim, GeneralJob* job, bool luma = false, int elemBytes = 1,
-                    const ssimk::ExchangeParams* xchg = nullptr)
+                    const ssimk::ExchangeParams* xchg = nullptr, bool deferMapReturn = false)
 {
     DEVICE_GUARD(c->device);
     cudaStream_t s = c->stream;
@@ -580,20 +586,33 @@ int enqueue_general(Context* c, uint32_t W, uint32_t srcRows, uint32_t outY0, ui
 
     job->c = c; job->W = W; job->outRows = outRows; job->map = map; job->mapStep = mapStep; job->mapStride = mapStride;
     job->cpuScatter = false;
-    if (map && !mapDirect) {
-        if (mapWhere == Where::Device) {
-            CU_TRY(ssimk::launch_scatter_map(s, map, mapStep, mapStride, dMap, (long long)dMapPitch, (int)W, (int)outRows));
-        } else if (mapStep == 1 && mapStride >= (ptrdiff_t)W) {
-            CU_TRY(cudaMemcpy2DAsync(map, (size_t)mapStride * sizeof(float), dMap, dMapPitch * sizeof(float), (size_t)W * sizeof(float),
-                                     outRows, cudaMemcpyDeviceToHost, s));
-        } else {
-            // strided / bottom-up host map: dense copy to pinned staging, scattered by the CPU in finish_general(),
-            // touching only the addressed floats (interleaved neighbours stay untouched, as in src/ssim.cpp:661-667)
-            if ((rc = c->stage.ensure((size_t)W * outRows * sizeof(float)))) return rc;
-            CU_TRY(cudaMemcpy2DAsync(c->stage.ptr, (size_t)W * sizeof(float), dMap, dMapPitch * sizeof(float), (size_t)W * sizeof(float),
-                                     outRows, cudaMemcpyDeviceToHost, s));
-            job->cpuScatter = true;
-        }
+    job->dMap = dMap; job->dMapPitch = dMapPitch; job->mapDirect = mapDirect; job->mapOnDevice = mapWhere == Where::Device;
+    // A device-to-host copy into pageable memory blocks the calling thread until the kernel before it has finished: callers
+    // that still have kernels to launch on OTHER devices which this kernel waits for (strips exchanged over peer memory)
+    // defer the map's return until everything is launched.
+    return deferMapReturn ? 0 : return_map(job);
+}
+
+int return_map(GeneralJob* job)
+{
+    if (!job->map || job->mapDirect) return 0;
+    Context* c = job->c;
+    DEVICE_GUARD(c->device);
+    cudaStream_t s = c->stream;
+    const uint32_t W = job->W, outRows = job->outRows;
+    int rc;
+    if (job->mapOnDevice) {
+        CU_TRY(ssimk::launch_scatter_map(s, job->map, job->mapStep, job->mapStride, job->dMap, (long long)job->dMapPitch, (int)W, (int)outRows));
+    } else if (job->mapStep == 1 && job->mapStride >= (ptrdiff_t)W) {
+        CU_TRY(cudaMemcpy2DAsync(job->map, (size_t)job->mapStride * sizeof(float), job->dMap, job->dMapPitch * sizeof(float), (size_t)W * sizeof(float),
+                                 outRows, cudaMemcpyDeviceToHost, s));
+    } else {
+        // strided / bottom-up host map: dense copy to pinned staging, scattered by the CPU in finish_general(),
+        // touching only the addressed floats (interleaved neighbours stay untouched, as in src/ssim.cpp:661-667)
+        if ((rc = c->stage.ensure((size_t)W * outRows * sizeof(float)))) return rc;
+        CU_TRY(cudaMemcpy2DAsync(c->stage.ptr, (size_t)W * sizeof(float), job->dMap, job->dMapPitch * sizeof(float), (size_t)W * sizeof(float),
+                                 outRows, cudaMemcpyDeviceToHost, s));
+        job->cpuScatter = true;
     }
     return 0;
 }
@@ -911,7 +930,12 @@ int compute_strips(int n, const int* devices, uint32_t W, uint32_t H, const uint
         const uint32_t s0 = y0 >= (uint32_t)ssimk::kHalo ? y0 - ssimk::kHalo : 0, s1 = std::min<uint64_t>(H, (uint64_t)y1 + ssimk::kHalo);
         rc = enqueue_general(ctx[g], W, s1 - s0, y0 - s0, y1 - y0, a + (ptrdiff_t)s0 * strideA, stepA, strideA, b + (ptrdiff_t)s0 * strideB,
                              stepB, strideB, map ? map + (ptrdiff_t)y0 * mapStride : nullptr, mapStep, mapStride, false, &jobs[g], false, 1,
-                             x.world ? &x : nullptr);
+                             x.world ? &x : nullptr, /*deferMapReturn*/ true);
+        if (rc) return fail_all(rc);
+    }
+    // every GPU's kernel is launched: now the maps may start flowing back (see enqueue_general)
+    for (int g = 0; g < n; ++g) {
+        int rc = return_map(&jobs[g]);
         if (rc) return fail_all(rc);
     }
     // where the total ends up on device 0: the exchange wrote it (and a status word) to chunkSums, NCCL reduces scalars in place
