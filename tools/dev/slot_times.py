@@ -34,14 +34,12 @@ def run(W, H, F, with_map=True):
     print()
     # first half of the CTAs (launched first) vs second half
     cta = np.arange(len(t)) // PAIRS
-    print("   CTAs 0-147 finish median %.1f, CTAs 148-295 finish median %.1f" % (np.median(end[cta < 148]), np.median(end[cta >= 148])))
+    per_cta = [float(np.median(end[cta == c])) for c in range(int(cta.max()) + 1)]
+    print("   finish per CTA (median of its pairs):", " ".join("%.0f" % v for v in per_cta))
     order = np.argsort(-end)[:12]
     print("   slowest slots (slot: start, finish us):", " ".join("%d: %.1f-%.1f" % (i, start[i], end[i]) for i in order))
-    # progress: time (us) at which the k-th ring unit (8 rows) was finished, median over the slots of each half of the grid
-    u = (full[:, 2:] - t0) / 1e3
-    for name, sel in (("first CTAs ", cta < 148), ("second CTAs", cta >= 148)):
-        cols = [k for k in range(u.shape[1]) if (full[sel][:, 2 + k] > 0).mean() > 0.9]
-        print("   %s unit finish times:" % name, " ".join("%.1f" % np.median(u[sel][:, k]) for k in cols[:24]))
+
 run(3840, 2160, 1)
 run(3840, 2160, 16)
+run(3840, 2160, 64)
 run(1920, 1080, 1, False)
