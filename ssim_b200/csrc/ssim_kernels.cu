@@ -166,7 +166,8 @@ constexpr uint32_t kBarTmaFull = 0, kBarStageEmpty = 16, kBarRingFull = 32, kBar
 // ---- producer: TMA + horizontal pass
 template <bool kU16>
 __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUtensorMap* tmB, const FusedParams& p, int lane,
-                                              uint32_t pairSmem, uint32_t barBase, PieceCursor cur, const PieceGeo& g0, float ca0, float cb0)
+                                              uint32_t pairSmem, uint32_t barBase, PieceCursor cur, const PieceGeo& g0, float ca0, float cb0,
+                                              bool have1, const PieceGeo& g1, float ca1, float cb1)
 {
     typedef PixGeo<kU16> G;
     constexpr int kBoxW = G::kBoxBytes, kImgStageBytes = G::kImgStageBytes, kStageBytes = G::kStageBytes;
@@ -202,11 +203,11 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             tma_load_3d(dst + kImgStageBytes, tmB, ge.bx - G::kBoxLeftElems, y0, ge.frame, bar);
         }
     };
-    PieceGeo g, gN = g0;                                    // the slot's first piece: found by the kernel's common prologue
-    float ca, cb, caN = ca0, cbN = cb0;
-    bool haveN;
+    PieceGeo g = g0, gN = g1;                               // the slot's first two pieces: found by the kernel's common prologue
+    float ca = ca0, cb = cb0, caN = ca1, cbN = cb1;
+    bool haveN = have1;
     #pragma unroll 1
-    for (int b = 0; b < kStages; ++b) issue(gN, b, (uint32_t)b, false, 0, false);
+    for (int b = 0; b < kStages; ++b) issue(g, b, (uint32_t)b, false, 0, false);
 
     const uint32_t magic = p.magic;                    // 0x4B000000, passed as a parameter so that it lives in a register and
                                                        // PRMT takes the byte selector as its immediate (no per-PRMT selector MOV)
@@ -239,14 +240,6 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     uint32_t released = 0;                                  // ring halves (global count) handed to the consumer
     #pragma unroll 1
     for (;;) {
-        // the piece fetched one ahead becomes the current one; fetch the next (the only copy of this code: what sits
-        // between the consumer's body and the block loop below in the binary is cold code inside the hot address range)
-        g = gN; ca = caN; cb = cbN;
-        {
-            Piece pc;
-            haveN = cursor_next(cur, p.geo, pc);
-            if (haveN) { piece_geo(p, pc, gN); piece_centre<kU16>(p, gN, caN, cbN); }
-        }
         // (a - ca, b - cb) from the bytes: PRMT builds 2^23 + byte, one packed FADD removes 2^23 + centre (exact)
         const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));
         const float k2 = -0.5f * p.eps2 * (ca - cb) * (ca - cb);  // see the formula in consumer_warp()
@@ -383,6 +376,13 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
         }
         firstHalf += ((uint32_t)g.nRows + kTaps - 1) / kTaps;
         if (!haveN) break;
+        // the piece fetched one ahead becomes the current one; fetch the next.  (This code sits BEHIND the block loop in the
+        // binary; its first two executions were moved into the kernel's common prologue so that no cold code lies between the
+        // consumer's body and the block loop.)
+        g = gN; ca = caN; cb = cbN;
+        Piece pc;
+        haveN = cursor_next(cur, p.geo, pc);
+        if (haveN) { piece_geo(p, pc, gN); piece_centre<kU16>(p, gN, caN, cbN); }
     }
     #undef TAP
 }
@@ -692,19 +692,22 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // hot address range, which then no longer fits the 32 KB instruction cache behind the L0s (stall_no_instruction 8% of
     // the samples against 2% when the two hot loops are nearly adjacent).  The empty volatile asm pins the values here.
     PieceCursor cur0;
-    PieceGeo g0 = PieceGeo();
-    float ca0 = 0.f, cb0 = 0.f;
-    int have0 = 0;
+    PieceGeo g0 = PieceGeo(), g1 = PieceGeo();
+    float ca0 = 0.f, cb0 = 0.f, ca1 = 0.f, cb1 = 0.f;
+    int have0 = 0, have1 = 0;
     if (slot < p.geo.slots) {
         cursor_init(cur0, p.geo, slot);
         Piece pc;
         have0 = cursor_next(cur0, p.geo, pc) ? 1 : 0;
         if (have0) { piece_geo(p, pc, g0); piece_centre<kU16>(p, g0, ca0, cb0); }
+        have1 = have0 && cursor_next(cur0, p.geo, pc) ? 1 : 0;
+        if (have1) { piece_geo(p, pc, g1); piece_centre<kU16>(p, g1, ca1, cb1); }
     } else {
         cur0.q = cur0.qEnd = cur0.colBase = 0; cur0.frame = cur0.band = 0;
     }
-    asm volatile("" : "+r"(cur0.q), "+r"(cur0.qEnd), "+r"(cur0.colBase), "+r"(cur0.frame), "+r"(cur0.band), "+r"(have0));
+    asm volatile("" : "+r"(cur0.q), "+r"(cur0.qEnd), "+r"(cur0.colBase), "+r"(cur0.frame), "+r"(cur0.band), "+r"(have0), "+r"(have1));
     asm volatile("" : "+r"(g0.frame), "+r"(g0.bx), "+r"(g0.oy0), "+r"(g0.nOut), "+r"(g0.inY0), "+r"(g0.nRows), "+r"(g0.nBlk), "+f"(ca0), "+f"(cb0));
+    asm volatile("" : "+r"(g1.frame), "+r"(g1.bx), "+r"(g1.oy0), "+r"(g1.nOut), "+r"(g1.inY0), "+r"(g1.nRows), "+r"(g1.nBlk), "+f"(ca1), "+f"(cb1));
 
     if (isConsumer) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kConsumerRegs));
@@ -713,7 +716,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kProducerRegs));
         if (slot >= p.geo.slots || !have0) return;          // a slot without any output row
-        producer_warp<kU16>(&tmA, &tmB, p, lane, pairSmem, barBase, cur0, g0, ca0, cb0);
+        producer_warp<kU16>(&tmA, &tmB, p, lane, pairSmem, barBase, cur0, g0, ca0, cb0, have1 != 0, g1, ca1, cb1);
     }
 }
 
