@@ -370,8 +370,9 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             // cumulativity.  Halves completely written so far; the piece's last block also completes its last, partial half.
             const uint32_t nBodies = ((uint32_t)g.nRows + kTaps - 1) / kTaps;
             const uint32_t complete = firstHalf + (blk + 1 == g.nBlk ? nBodies : min(((uint32_t)blk * kBlkRows + kBlkRows) / kTaps, nBodies));
-            for (uint32_t h = released; h < complete; ++h) mbar_arrive(barFull + 8 * (h & 1u));
-            released = max(released, complete);
+            // (a block completes at most two halves: 8 rows of its own plus, in a piece's last block, the partial last half)
+            if (released < complete) { mbar_arrive(barFull + 8 * (released & 1u)); ++released; }
+            if (released < complete) { mbar_arrive(barFull + 8 * (released & 1u)); ++released; }
             ++gblk;
         }
         firstHalf += ((uint32_t)g.nRows + kTaps - 1) / kTaps;
