@@ -54,6 +54,13 @@ __device__ __forceinline__ void stg_f32(unsigned long long addr, float v) {
     asm volatile("st.global.f32 [%0+%1], %2;" :: "l"(addr), "n"(kOff), "f"(v) : "memory");
 }
 
+// predicated store, the predicate travelling as a register (flag != 0): one SETP + one predicated STG, no branch, and the
+// compiler cannot re-derive the column test from the lane index in every row
+template <int kOff>
+__device__ __forceinline__ void stg_f32_if(unsigned long long addr, float v, uint32_t flag) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q st.global.f32 [%0+%1], %2;\n}\n" :: "l"(addr), "n"(kOff), "f"(v), "r"(flag) : "memory");
+}
+
 // "if (pred) { store v; sum += v; }" as ONE predicate and two predicated instructions (no branch): the predicate travels as a
 // register between rows; kStore = false leaves only the predicated add
 template <int kOff, bool kStore>
@@ -611,7 +618,9 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
         piece_centre<kU16>(p, g, ca, cb);
         const bool colOk0 = g.bx + lane < p.width;
         const bool colOk1 = g.bx + 32 + lane < p.width;
-        const bool fullBand = g.bx + kBandW <= p.width;                 // warp-uniform: no column predicates needed
+        // column tests as opaque flags in registers: ptxas otherwise re-derives them from the lane index in every row
+        uint32_t okFlag0 = colOk0 ? 1u : 0u, okFlag1 = colOk1 ? 1u : 0u, fullFlag = g.bx + kBandW <= p.width ? 1u : 0u;
+        asm volatile("" : "+r"(okFlag0), "+r"(okFlag1), "+r"(fullFlag));
         // Map addressing: one 64-bit per-lane address that advances by the pitch per input row (starts 10 rows above the
         // piece, never dereferenced there); the second column is an immediate offset.  Stores are written in PTX so
         // that the address arithmetic stays these two adds per row.
@@ -638,11 +647,10 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
                 const int i = iBase + t;
                 if (i >= 2 * kHalo && i < nRows) {                      // warp-uniform: the row completes a wanted output
                     if (kMap == 1) {
-                        if (fullBand) { stg_f32<0>(mapAddr, sv0); stg_f32<128>(mapAddr, sv1); }
-                        else {
-                            if (colOk0) stg_f32<0>(mapAddr, sv0);
-                            if (colOk1) stg_f32<128>(mapAddr, sv1);
-                        }
+                        // two predicated stores; a separate unpredicated path for bands that lie fully inside the
+                        // plane would double the store code of all 11 unrolled rows (hot code size matters: see the kernel)
+                        if (fullFlag) { stg_f32<0>(mapAddr, sv0); stg_f32<128>(mapAddr, sv1); }
+                        else { stg_f32_if<0>(mapAddr, sv0, okFlag0); stg_f32_if<128>(mapAddr, sv1, okFlag1); }
                     }
                     if (kMap == 2) {
                         if (colOk0) stg_f32<0>(mapAddr, sv0);
