@@ -688,6 +688,12 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_proxy_async();
     }
     __syncthreads();                                                    // the only CTA-wide barrier
+    // Programmatic dependent launch (launch_fused sets the stream-serialization attribute): the next launch on the stream may
+    // be scheduled while this grid runs -- its CTAs move onto the SMs as ours leave and get as far as this point -- and
+    // everything that touches memory waits here until the launch before this one has completed and flushed.  Takes the launch
+    // latency out of calls queued back to back; without the attribute both instructions do nothing.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t slot = blockIdx.x * kPairsPerCta + pair;
     const uint32_t pairSmem = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + pair * PixGeo<kU16>::kPairSmemBytes;
@@ -850,16 +856,19 @@ cudaError_t launch_fused(cudaStream_t stream, const CUtensorMap& tmA, const CUte
     ExchangeParams none;
     if (!xchg) { memset(&none, 0, sizeof(none)); xchg = &none; }
     const int mapKind = !p.map ? 0 : p.mapStep == 1 ? 1 : 2;
-    if (p.u16) {
-        if (mapKind == 2) return cudaErrorInvalidValue;              // 16-bit pixels: dense maps only
-        if (mapKind) ssim_fused_kernel<1, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else         ssim_fused_kernel<0, true><<<ctas, kCtaThreads, PixGeo<true>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-    } else {
-        if (mapKind == 2)      ssim_fused_kernel<2, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else if (mapKind == 1) ssim_fused_kernel<1, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-        else                   ssim_fused_kernel<0, false><<<ctas, kCtaThreads, PixGeo<false>::kCtaSmemBytes, stream>>>(tmA, tmB, p, *xchg);
-    }
-    return cudaGetLastError();
+    if (p.u16 && mapKind == 2) return cudaErrorInvalidValue;         // 16-bit pixels: dense maps only
+    typedef void (*Kernel)(const CUtensorMap, const CUtensorMap, const FusedParams, const ExchangeParams);
+    const Kernel kernel = p.u16 ? (mapKind ? ssim_fused_kernel<1, true> : ssim_fused_kernel<0, true>)
+                                : (mapKind == 2 ? ssim_fused_kernel<2, false> : mapKind == 1 ? ssim_fused_kernel<1, false> : ssim_fused_kernel<0, false>);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kCtaThreads);
+    cfg.dynamicSmemBytes = p.u16 ? PixGeo<true>::kCtaSmemBytes : PixGeo<false>::kCtaSmemBytes;
+    cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p, *xchg);
 }
 
 cudaError_t fused_kernel_attributes(int* regsMap, int* regsNoMap, int* pairsPerSm)
