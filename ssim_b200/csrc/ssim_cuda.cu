@@ -229,7 +229,6 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {             // reduction workspace of one stream, see get_workspace()
     Buffer buf;
-    size_t counters = 0;       // capacity of the counter region, in frames
 };
 
 struct Context {
@@ -377,12 +376,13 @@ bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frame
     return ssimk::plan_slots((uint32_t)(c->numSMs * pairs), width, outRows, frames, minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan);
 }
 
-// Reduction workspace of a stream: per-frame arrival counters (zero between launches: the kernel resets them), then
-// slots*entries doubles.  Launches on one stream run in order, so they can share it.  A workspace that has become too
-// small is retired, not freed: work queued earlier on the stream may still be using it.
-struct WorkspaceView { unsigned* frameDone; double* partials; };
+// Reduction workspace of a stream: slots*entries doubles, every one holding the "empty" pattern (all ones) between
+// launches -- it is filled once here, and the kernel's reducer puts the pattern back into every entry it has read.
+// Launches on one stream run in order, so they can share it.  A workspace that has become too small is retired, not
+// freed: work queued earlier on the stream may still be using it.
+struct WorkspaceView { double* partials; };
 
-int get_workspace(Context* c, cudaStream_t stream, size_t frames, size_t cells, WorkspaceView* out)
+int get_workspace(Context* c, cudaStream_t stream, size_t cells, WorkspaceView* out)
 {
     std::lock_guard<std::mutex> lock(c->wsMutex);
     auto it = c->workspaces.find(stream);
@@ -398,16 +398,14 @@ int get_workspace(Context* c, cudaStream_t stream, size_t frames, size_t cells, 
         it = c->workspaces.emplace(stream, Workspace()).first;
     }
     Workspace& w = it->second;
-    if (frames > w.counters || w.counters * sizeof(unsigned) + cells * sizeof(double) > w.buf.cap) {
+    if (cells * sizeof(double) > w.buf.cap) {
         if (w.buf.ptr) { c->retired.push_back(w.buf.ptr); w.buf.ptr = nullptr; w.buf.cap = 0; }
-        w.counters = align_up(std::max<size_t>(2 * frames, 1024), 4);
-        const size_t bytes = w.counters * sizeof(unsigned) + std::max<size_t>(2 * cells, 4096) * sizeof(double);
+        const size_t bytes = std::max<size_t>(2 * cells, 4096) * sizeof(double);
         int rc = w.buf.ensure(bytes);
-        if (rc) { w.counters = 0; return rc; }
-        CU_TRY(cudaMemsetAsync(w.buf.ptr, 0, w.counters * sizeof(unsigned), stream));
+        if (rc) return rc;
+        CU_TRY(cudaMemsetAsync(w.buf.ptr, 0xff, w.buf.cap, stream));
     }
-    out->frameDone = (unsigned*)w.buf.ptr;
-    out->partials = (double*)((char*)w.buf.ptr + w.counters * sizeof(unsigned));
+    out->partials = (double*)w.buf.ptr;
     return 0;
 }
 
@@ -432,7 +430,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (!plan_for(c, width, outRows, frames, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
 
     WorkspaceView ws;
-    int rc = get_workspace(c, stream, frames, (size_t)plan.slots * plan.entries, &ws);
+    int rc = get_workspace(c, stream, (size_t)plan.slots * plan.entries, &ws);
     if (rc) return rc;
     const CUtensorMap *tmA, *tmB;
     if ((rc = get_plane_map(&tmA, dA, width, srcRows, frames, pitchA, frameStrideA, elemBytes))) return rc;
@@ -447,7 +445,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride; p.mapStep = (long long)mapStep;
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.geo = ssimk::make_slot_geo(plan, width);
-    p.partials = ws.partials; p.frameDone = ws.frameDone; p.entries = plan.entries;
+    p.partials = ws.partials; p.entries = plan.entries;
     p.sums = dSums; p.ssim = dSsim;
     p.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];

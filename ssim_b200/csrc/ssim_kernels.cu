@@ -395,10 +395,18 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     #undef TAP
 }
 
-// ---- reduction: per-frame arrival counters; the LAST slot to deliver its partial sum of a frame adds that frame's partials
-// up in slot order (fixed order => deterministic) -- frames of a batch are reduced while the rest of the grid still
-// computes, a single image by whichever consumer warp finishes last.  Strips across GPUs: that warp also exchanges the strip
-// sums with the peers.
+// ---- reduction: no counters, no atomics, no fences.  Every slot stores its partial sum of a frame into its own entry of the
+// workspace with ONE relaxed 64-bit store; an entry that has not been written yet holds kEmptyEntry (all ones, a NaN no sum
+// can be: NaN sums are canonicalised).  The REDUCER of a frame is member 0 of the first team whose units touch the frame: the
+// frame's rows are the last thing in that team's range (or the team owns the whole frame), so by the time it gets there the
+// other slots have normally delivered long ago.  It loads all entries of the frame in one batch (the L2 latencies overlap),
+// repeats the batch while any entry is still empty, adds them up in slot order (fixed order => deterministic), and writes
+// kEmptyEntry back so that the workspace is clean for the next launch on the stream.  (The earlier protocol -- partial, fence,
+// atomic counter, last arriver reduces -- put ~4.5 us behind the last row of a single image: the fence waits for the
+// slot's map stores, then the atomic's round trip, then the loads.)  Strips across GPUs: the reducer also exchanges the
+// strip sums with the peers.
+constexpr unsigned long long kEmptyEntry = 0xffffffffffffffffull;
+
 __device__ __forceinline__ double warp_sum(double v)
 {
     #pragma unroll
@@ -412,43 +420,78 @@ __device__ __forceinline__ uint32_t share_of_unit(const SlotGeo& g, uint32_t q)
     return q < big ? q / (g.shareQ + 1u) : g.shareR + (q - big) / g.shareQ;
 }
 
-// Slot `slot` has written its entry for frame f (entry index = f - first frame its unit range touches; slots that hold
-// none of the frame's rows deliver 0) and now arrives at the frame's counter: threadFenceReduction pattern.
-__device__ __forceinline__ void frame_arrive(const FusedParams& p, const ExchangeParams& x, int f, int lane)
+__device__ __forceinline__ void entry_store(double* entry, double v)
+{
+    unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    if (v != v) bits = 0x7ff8000000000000ull;           // any NaN -> the canonical quiet NaN, never kEmptyEntry
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(entry), "l"(bits) : "memory");
+}
+__device__ __forceinline__ unsigned long long entry_load(const double* entry)
+{
+    unsigned long long bits;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(entry) : "memory");
+    return bits;
+}
+
+// Called by the reducer of frame f (see above) after it has stored its own entry.
+__device__ __forceinline__ void frame_reduce(const FusedParams& p, const ExchangeParams& x, int f, int lane)
 {
     const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
     const uint32_t u0 = (uint32_t)f * frameUnits, u1 = u0 + frameUnits;
     // the slots that deliver to this frame are the members of the teams whose units intersect the frame's: a contiguous
-    // run [sLo, sHi] (members without a band there deliver zeros)
-    const uint32_t sLo = share_of_unit(p.geo, u0) * p.geo.group, sHi = (share_of_unit(p.geo, u1 - 1u) + 1u) * p.geo.group - 1u;
-    __threadfence();
-    unsigned prev = 0;
-    if (lane == 0) prev = atomicAdd(p.frameDone + f, 1u);
-    prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev != sHi - sLo) return;                      // not the last of the sHi - sLo + 1 slots
-    __threadfence();
-    // fixed order (slot order, lanes strided, then the shuffle tree): deterministic.  The loads are issued in batches so
-    // that their L2 latencies overlap (one dependent load per add cost 13 us for the 1184 partials of a single frame).
+    // run [sLo, sHi] (members without a band there deliver zeros).  Entry index = f - first frame of the slot's range: 0 for
+    // every team but the first, whose range may start in an earlier frame.
+    const uint32_t tLo = share_of_unit(p.geo, u0);
+    const uint32_t sLo = tLo * p.geo.group, sHi = (share_of_unit(p.geo, u1 - 1u) + 1u) * p.geo.group - 1u;
+    uint32_t eLo;
+    { uint32_t q0, q1; slot_units(p.geo, sLo, q0, q1); eLo = (uint32_t)f - q0 / frameUnits; }
     double acc = 0.0;
-    constexpr int kBatch = 40;                          // one batch covers the 8 x 148 partials of a single frame
-    for (uint32_t s0 = sLo + lane; s0 <= sHi; s0 += 32 * kBatch) {
-        double v[kBatch];
+    constexpr int kBatch = 40;                          // one batch covers the 8 x 148 entries of a single frame
+    for (uint32_t sBase = sLo; sBase <= sHi; sBase += 32 * kBatch) {     // warp-uniform trip count (there are votes inside)
+        const uint32_t s0 = sBase + lane;
+        // One round = all of this lane's entries of the batch loaded at once (their L2 latencies overlap).  Normally the first
+        // round finds everything; otherwise polling rounds repeat until no entry is empty and the batch is loaded once more
+        // (values kept in registers across the polling loop cost MOVs in the 11-row body, of all places).
+        // Branch-free on purpose (lanes past the end re-read the last entry), and every decision is a VOTE.ALL predicate:
+        // with a per-lane branch in here, or a ballot/any deciding a loop exit, ptxas no longer proves the warp converged
+        // afterwards and wraps every branch of the 11-row body in BSSY/BSYNC (+10% instructions there).
+        unsigned long long v[kBatch];
+        bool missing = false;
         #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
             const uint32_t s = s0 + 32u * k;
-            v[k] = 0.0;
-            if (s <= sHi) {
-                uint32_t e = 0;                                                             // a single frame: entries == 1
-                if (p.frames != 1) { uint32_t q0, q1; slot_units(p.geo, s, q0, q1); e = (uint32_t)f - q0 / frameUnits; }
-                v[k] = __ldcg(p.partials + (size_t)s * p.entries + e);
+            v[k] = 0ull;
+            if (s <= sHi) v[k] = entry_load(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u));
+        }
+        #pragma unroll
+        for (int k = 0; k < kBatch; ++k) missing |= (v[k] == kEmptyEntry);
+        if (!__all_sync(0xffffffffu, !missing)) {
+            bool allThere;
+            do {
+                unsigned miss = 0u;
+                #pragma unroll 20
+                for (int k = 0; k < kBatch; ++k) {
+                    const uint32_t s = min(s0 + 32u * k, sHi);
+                    miss |= (entry_load(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u)) == kEmptyEntry) ? 1u : 0u;
+                }
+                allThere = __all_sync(0xffffffffu, miss == 0u);
+            } while (!allThere);
+            #pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const uint32_t s = s0 + 32u * k;
+                v[k] = 0ull;
+                if (s <= sHi) v[k] = entry_load(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u));
             }
         }
         #pragma unroll
-        for (int k = 0; k < kBatch; ++k) acc += v[k];
+        for (int k = 0; k < kBatch; ++k) {
+            const uint32_t s = s0 + 32u * k;
+            acc += __longlong_as_double((long long)v[k]);
+            if (s <= sHi) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u)), "l"(kEmptyEntry) : "memory");
+        }
     }
     acc = warp_sum(acc);
     if (lane == 0) {
-        p.frameDone[f] = 0u;                            // ready for the next launch on this stream
         if (p.sums) p.sums[f] = acc;
         if (p.ssim) p.ssim[f] = (float)(acc * p.invCount);
     }
@@ -596,12 +639,13 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
         const int f = have ? pc.frame : fLast + 1;
         if (f != curFrame) {
             // the slot moves on to another frame (or is done): deliver curFrame's sum, and zeros for frames whose units
-            // here held no rows, each followed by the arrival at the frame's counter (the one call site of frame_arrive)
+            // here held no rows
             double v = warp_sum(total);
             #pragma unroll 1
             for (; curFrame < f; ++curFrame) {
-                if (lane == 0 && (uint32_t)(curFrame - fFirst) < p.entries) myPart[curFrame - fFirst] = v;
-                frame_arrive(p, x, curFrame, lane);
+                if (lane == 0 && (uint32_t)(curFrame - fFirst) < p.entries) entry_store(myPart + (curFrame - fFirst), v);
+                // member 0 of the first team that touches the frame reduces it (the one call site of frame_reduce)
+                if (slot == share_of_unit(p.geo, (uint32_t)curFrame * frameUnits) * p.geo.group) frame_reduce(p, x, curFrame, lane);
                 v = 0.0;
             }
             total = 0.0;

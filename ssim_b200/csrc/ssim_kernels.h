@@ -199,9 +199,8 @@ struct FusedParams {
     int width, srcRows, outY0, outRows, frames;
     SlotGeo geo;
     // reduction workspace (per stream): partial sums [slots][entries] (entry e of slot s belongs to frame
-    // e + the first frame whose units s owns) and one arrival counter per frame
+    // e + the first frame whose units s owns); all ones ("empty") before the launch and again after it
     double*   partials;
-    unsigned* frameDone;     // [frames], zero before the launch; the last slot to arrive at a frame reduces it and resets it
     uint32_t  entries;
     double*   sums;          // out, may be NULL: [frames] sum of the SSIM values of each frame
     float*    ssim;          // out, may be NULL: [frames] float(sum * invCount)
