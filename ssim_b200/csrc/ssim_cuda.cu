@@ -445,7 +445,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride; p.mapStep = (long long)mapStep;
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.geo = ssimk::make_slot_geo(plan, width);
-    p.partials = ws.partials; p.entries = plan.entries;
+    p.partials = ws.partials; p.entries = plan.entries; p.reducerSlot = plan.reducerSlot;
     p.sums = dSums; p.ssim = dSsim;
     p.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];

@@ -644,8 +644,9 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
             #pragma unroll 1
             for (; curFrame < f; ++curFrame) {
                 if (lane == 0 && (uint32_t)(curFrame - fFirst) < p.entries) entry_store(myPart + (curFrame - fFirst), v);
-                // member 0 of the first team that touches the frame reduces it (the one call site of frame_reduce)
-                if (slot == share_of_unit(p.geo, (uint32_t)curFrame * frameUnits) * p.geo.group) frame_reduce(p, x, curFrame, lane);
+                // member 0 of the first team that touches the frame reduces it (the one call site of frame_reduce); for a single
+                // frame the host names the slot it expects to finish last, so that the reducer finds all entries at once
+                if (slot == (p.frames == 1 ? p.reducerSlot : share_of_unit(p.geo, (uint32_t)curFrame * frameUnits) * p.geo.group)) frame_reduce(p, x, curFrame, lane);
                 v = 0.0;
             }
             total = 0.0;

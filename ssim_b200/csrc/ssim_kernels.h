@@ -80,9 +80,13 @@ struct SlotPlan {
     uint32_t slots;          // warp pairs that get work = teams * group
     uint32_t group;          // pairs per team = adjacent bands walked side by side
     uint32_t shareQ, shareR; // units per team: team j owns shareQ + (j < shareR) units
-    uint32_t colUnits;       // units per column = outRows + kPad
+    uint32_t colUnits;       // units per column = outRows + pad
+    uint32_t pad;            // padding units in front of every column: kPad, or more when the columns are cut into equal parts
     uint32_t entries;        // partial-sum entries per slot = max number of frames whose units one slot can own
+    uint32_t reducerSlot;    // single frame: a slot that is expected to finish last (it adds up the partial sums)
 };
+constexpr uint32_t kCrossingUnits = 9;   // what it costs a team to start a second piece (its range crosses into the next column),
+                                         // in row units: measured, the crossing teams of a 4K pair finish 3 us after the others
 
 // Pure host logic (unit-tested on the CPU: tests/clients/plan_check.cpp).  maxSlots: warp pairs resident at once (8 per SM).
 // minUnits: do not spread the work thinner than this many units per slot (tiny images would otherwise pay 10 start-up rows
@@ -105,16 +109,46 @@ inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint
         if (cost < bestCost - 1e-12) { bestCost = cost; bestG = g; }
     }
     const unsigned long long group = bestG, groupsPerFrame = (bands + group - 1) / group;
-    const unsigned long long units = groupsPerFrame * frames * colUnits;          // per team member
+    const unsigned long long cols = groupsPerFrame * frames;
+    unsigned long long units = cols * colUnits;                                    // per team member
+    const unsigned long long maxTeams = maxSlots / group;
     unsigned long long teams = units / minUnits;
-    if (teams > maxSlots / group) teams = maxSlots / group;
+    if (teams > maxTeams) teams = maxTeams;
     if (teams < 1) teams = 1;
-    plan->slots = (uint32_t)(teams * group);
     plan->group = (uint32_t)group;
+    plan->pad = kPad;
+    plan->colUnits = (uint32_t)colUnits;
+    plan->reducerSlot = 0;
+    // Few columns, many teams (a single image): cutting every column into k equal parts -- the column is padded up to
+    // k * Q units -- leaves some teams idle but spares all others the second piece that a range crossing a column boundary
+    // means.  Taken when it is the faster of the two by the model "time = units + start-up rows (+ a crossing)".
+    bool equalParts = false;
+    if (cols > 1 && cols <= maxTeams) {
+        unsigned long long k = maxTeams / cols;
+        while (k > 1 && (colUnits + k - 1) / k < minUnits) --k;
+        const unsigned long long partQ = (colUnits + k - 1) / k;
+        const unsigned long long lineQ = (units + teams - 1) / teams;
+        if (partQ >= minUnits && partQ < lineQ + kCrossingUnits && k * partQ * cols <= 0x7fffffffull) {
+            equalParts = true;
+            teams = k * cols;
+            plan->colUnits = (uint32_t)(k * partQ);
+            plan->pad = (uint32_t)(k * partQ - outRows);
+            units = cols * k * partQ;
+            if (k > 1) plan->reducerSlot = (uint32_t)group;             // the second team of the first column: a full part
+        }
+    }
+    plan->slots = (uint32_t)(teams * group);
     plan->shareQ = (uint32_t)(units / teams);
     plan->shareR = (uint32_t)(units % teams);
-    plan->colUnits = (uint32_t)colUnits;
-    const unsigned long long frameUnits = groupsPerFrame * colUnits;
+    if (!equalParts && frames == 1 && cols > 1) {
+        // the first team whose range crosses a column boundary and has output rows on both sides
+        for (unsigned long long t = 0; t < teams; ++t) {
+            const unsigned long long q0 = t * plan->shareQ + (t < plan->shareR ? t : plan->shareR), q1 = q0 + plan->shareQ + (t < plan->shareR ? 1 : 0);
+            const unsigned long long c1 = (q1 - 1) / colUnits;
+            if (q0 / colUnits != c1 && q1 - c1 * colUnits > (unsigned long long)kPad) { plan->reducerSlot = (uint32_t)(t * group); break; }
+        }
+    }
+    const unsigned long long frameUnits = groupsPerFrame * plan->colUnits;
     // a range of n units touches at most (n + frameUnits - 2) / frameUnits + 1 frames
     unsigned long long entries = ((unsigned long long)plan->shareQ + 1 + frameUnits - 2) / frameUnits + 1;
     if (entries > frames) entries = frames;
@@ -146,7 +180,7 @@ SSIMK_HD uint32_t ssimk_mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((unsi
 SSIMK_HD uint32_t ssimk_div(uint32_t n, uint32_t mul, uint32_t shift) { return mul ? ssimk_mulhi(n, mul) >> shift : n; }
 
 struct SlotGeo {             // the part of FusedParams the cursor needs (kept separate so that the CPU tests can build it)
-    uint32_t slots, group, groupsPerFrame, shareQ, shareR, colUnits, bands;
+    uint32_t slots, group, groupsPerFrame, shareQ, shareR, colUnits, pad, bands;
     uint32_t colMul, colShift;       // n / colUnits
     uint32_t gpfMul, gpfShift;       // n / groupsPerFrame
 };
@@ -175,8 +209,8 @@ SSIMK_HD bool cursor_next(PieceCursor& c, const SlotGeo& g, Piece& pc)
     while (c.q < c.qEnd) {
         const uint32_t ua = c.q - c.colBase;                                          // first unit inside the column
         const uint32_t ub = c.qEnd - c.colBase < g.colUnits ? c.qEnd - c.colBase : g.colUnits;
-        const int r0 = (int)(ua > (uint32_t)kPad ? ua - kPad : 0u);
-        const int r1 = (int)(ub > (uint32_t)kPad ? ub - kPad : 0u);
+        const int r0 = (int)(ua > g.pad ? ua - g.pad : 0u);
+        const int r1 = (int)(ub > g.pad ? ub - g.pad : 0u);
         pc.frame = c.frame; pc.band = c.band; pc.r0 = r0; pc.nOut = r1 - r0;
         const bool real = c.band < (int)g.bands;                                      // a ragged last group has members without a band
         c.colBase += g.colUnits;
@@ -202,6 +236,7 @@ struct FusedParams {
     // e + the first frame whose units s owns); all ones ("empty") before the launch and again after it
     double*   partials;
     uint32_t  entries;
+    uint32_t  reducerSlot;   // frames == 1: the slot that adds the partial sums up (any slot; best one that finishes last)
     double*   sums;          // out, may be NULL: [frames] sum of the SSIM values of each frame
     float*    ssim;          // out, may be NULL: [frames] float(sum * invCount)
     double    invCount;      // 1 / double(uint32(width*outRows))
@@ -228,7 +263,7 @@ inline void fast_div(uint32_t d, uint32_t* mul, uint32_t* shift)
 inline SlotGeo make_slot_geo(const SlotPlan& plan, uint32_t width)
 {
     SlotGeo g;
-    g.slots = plan.slots; g.group = plan.group; g.shareQ = plan.shareQ; g.shareR = plan.shareR; g.colUnits = plan.colUnits;
+    g.slots = plan.slots; g.group = plan.group; g.shareQ = plan.shareQ; g.shareR = plan.shareR; g.colUnits = plan.colUnits; g.pad = plan.pad;
     g.bands = (width + kBandW - 1) / kBandW;
     g.groupsPerFrame = (g.bands + g.group - 1) / g.group;
     fast_div(g.colUnits, &g.colMul, &g.colShift);
