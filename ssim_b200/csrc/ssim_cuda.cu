@@ -373,16 +373,15 @@ bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frame
     const int minRows = g_minSlotRows.load(std::memory_order_relaxed);
     int pairs = g_maxPairsPerSm.load(std::memory_order_relaxed);
     if (pairs <= 0 || pairs > c->pairsPerSm) pairs = c->pairsPerSm;
-    return ssimk::plan_slots((uint32_t)(c->numSMs * pairs), width, outRows, frames, minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan);
+    return ssimk::plan_slots(std::min<uint32_t>((uint32_t)(c->numSMs * pairs), ssimk::kMaxSlots), width, outRows, frames, minRows > 0 ? (uint32_t)minRows : kDefaultMinSlotRows, plan);
 }
 
-// Reduction workspace of a stream: slots*entries doubles, every one holding the "empty" pattern (all ones) between
-// launches -- it is filled once here, and the kernel's reducer puts the pattern back into every entry it has read.
-// Launches on one stream run in order, so they can share it.  A workspace that has become too small is retired, not
-// freed: work queued earlier on the stream may still be using it.
-struct WorkspaceView { double* partials; };
+// Reduction workspace of a stream: one 64-bit accumulator per frame, zero between launches -- cleared once here, and the
+// kernel puts every word it has finished back to zero.  Launches on one stream run in order, so they can share it.  A
+// workspace that has become too small is retired, not freed: work queued earlier on the stream may still be using it.
+struct WorkspaceView { unsigned long long* frameAcc; };
 
-int get_workspace(Context* c, cudaStream_t stream, size_t cells, WorkspaceView* out)
+int get_workspace(Context* c, cudaStream_t stream, size_t frames, WorkspaceView* out)
 {
     std::lock_guard<std::mutex> lock(c->wsMutex);
     auto it = c->workspaces.find(stream);
@@ -398,14 +397,14 @@ int get_workspace(Context* c, cudaStream_t stream, size_t cells, WorkspaceView* 
         it = c->workspaces.emplace(stream, Workspace()).first;
     }
     Workspace& w = it->second;
-    if (cells * sizeof(double) > w.buf.cap) {
+    if (frames * sizeof(unsigned long long) > w.buf.cap) {
         if (w.buf.ptr) { c->retired.push_back(w.buf.ptr); w.buf.ptr = nullptr; w.buf.cap = 0; }
-        const size_t bytes = std::max<size_t>(2 * cells, 4096) * sizeof(double);
+        const size_t bytes = std::max<size_t>(2 * frames, 1024) * sizeof(unsigned long long);
         int rc = w.buf.ensure(bytes);
         if (rc) return rc;
-        CU_TRY(cudaMemsetAsync(w.buf.ptr, 0xff, w.buf.cap, stream));
+        CU_TRY(cudaMemsetAsync(w.buf.ptr, 0, w.buf.cap, stream));
     }
-    out->partials = (double*)w.buf.ptr;
+    out->frameAcc = (unsigned long long*)w.buf.ptr;
     return 0;
 }
 
@@ -430,7 +429,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     if (!plan_for(c, width, outRows, frames, &plan)) return fail(EINVAL, "image or batch too large (more than 2^31 row units)");
 
     WorkspaceView ws;
-    int rc = get_workspace(c, stream, (size_t)plan.slots * plan.entries, &ws);
+    int rc = get_workspace(c, stream, frames, &ws);
     if (rc) return rc;
     const CUtensorMap *tmA, *tmB;
     if ((rc = get_plane_map(&tmA, dA, width, srcRows, frames, pitchA, frameStrideA, elemBytes))) return rc;
@@ -445,7 +444,15 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride; p.mapStep = (long long)mapStep;
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.geo = ssimk::make_slot_geo(plan, width);
-    p.partials = ws.partials; p.entries = plan.entries; p.reducerSlot = plan.reducerSlot;
+    p.frameAcc = ws.frameAcc;
+    {
+        // fixed-point format of the in-kernel reduction (see "reduction" in ssim_kernels.cu): every slot adds (its sum + bias)
+        // * 2^k to the 52-bit field of its frame; bias >= the pixels a slot can hold of one frame, k as large as fits
+        const double bias = ((double)plan.shareQ + 1.0) * ssimk::kBandW;
+        int k = 0;
+        while (k < 40 && (double)plan.slots * 2.0 * bias * std::ldexp(1.0, k + 2) < 4503599627370496.0) ++k;      // 2^52
+        p.accBias = bias; p.accScale = std::ldexp(1.0, k); p.accInvScale = std::ldexp(1.0, -k);
+    }
     p.sums = dSums; p.ssim = dSsim;
     p.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];

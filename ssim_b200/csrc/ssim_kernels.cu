@@ -395,17 +395,22 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     #undef TAP
 }
 
-// ---- reduction: no counters, no atomics, no fences.  Every slot stores its partial sum of a frame into its own entry of the
-// workspace with ONE relaxed 64-bit store; an entry that has not been written yet holds kEmptyEntry (all ones, a NaN no sum
-// can be: NaN sums are canonicalised).  The REDUCER of a frame is member 0 of the first team whose units touch the frame: the
-// frame's rows are the last thing in that team's range (or the team owns the whole frame), so by the time it gets there the
-// other slots have normally delivered long ago.  It loads all entries of the frame in one batch (the L2 latencies overlap),
-// repeats the batch while any entry is still empty, adds them up in slot order (fixed order => deterministic), and writes
-// kEmptyEntry back so that the workspace is clean for the next launch on the stream.  (The earlier protocol -- partial, fence,
-// atomic counter, last arriver reduces -- put ~4.5 us behind the last row of a single image: the fence waits for the
-// slot's map stores, then the atomic's round trip, then the loads.)  Strips across GPUs: the reducer also exchanges the
-// strip sums with the peers.
-constexpr unsigned long long kEmptyEntry = 0xffffffffffffffffull;
+// ---- reduction: ONE 64-bit atomic per slot and frame, and nothing else.  Every frame owns one word of the workspace: the
+// low 52 bits accumulate the slots' sums in fixed point, the high 12 bits count the slots that have delivered.  A slot adds
+// (1 << 52) | fixed(sum + bias) with one atomicAdd; atomics on one address are totally ordered and return the old value, so
+// the slot whose atomic returns count == expected - 1 holds the frame's total in (old + own) -- no fence, no second counter,
+// nothing to poll -- and finishes the frame: result out, word back to zero for the next launch on the stream.  Integer
+// addition is associative, so the total does not depend on the order in which the slots arrive: the result is deterministic
+// (and, up to the rounding of each slot's sum to the fixed-point grid, independent of how the work was partitioned).
+// bias: SSIM values may be negative (> -1); every slot adds p.accBias >= its number of pixels so that what goes into the
+// field is non-negative, and the finisher takes expected * bias off again.  Scale: p.accScale = 2^k with k chosen by the
+// host so that the field cannot overflow 52 bits (4K frame: k = 27, i.e. 7e-9 per slot; the rounding of all slots together
+// moves the mean SSIM of a 4K frame by < 1e-12).
+// (Protocols tried before: partial sums in memory + fence + atomic counter + the last arriver adds them up: 4.5 us behind
+// the last row of a single image -- the fence waits for the slot's map stores, then the atomic's round trip, then 1184
+// loads; per-slot entries polled by a designated reducer: 4 us, the polling rounds are two dependent groups of loads.)
+// Strips across GPUs: the finishing slot also exchanges the strip sums with the peers.
+constexpr unsigned long long kAccCountShift = 52, kAccSumMask = (1ull << kAccCountShift) - 1ull;
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -420,78 +425,27 @@ __device__ __forceinline__ uint32_t share_of_unit(const SlotGeo& g, uint32_t q)
     return q < big ? q / (g.shareQ + 1u) : g.shareR + (q - big) / g.shareQ;
 }
 
-__device__ __forceinline__ void entry_store(double* entry, double v)
+// Slot delivers v = its sum of frame f's values (0 when its units there held no rows).
+__device__ __forceinline__ void frame_deliver(const FusedParams& p, const ExchangeParams& x, int f, double v, int lane)
 {
-    unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    if (v != v) bits = 0x7ff8000000000000ull;           // any NaN -> the canonical quiet NaN, never kEmptyEntry
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(entry), "l"(bits) : "memory");
-}
-__device__ __forceinline__ unsigned long long entry_load(const double* entry)
-{
-    unsigned long long bits;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(entry) : "memory");
-    return bits;
-}
-
-// Called by the reducer of frame f (see above) after it has stored its own entry.
-__device__ __forceinline__ void frame_reduce(const FusedParams& p, const ExchangeParams& x, int f, int lane)
-{
-    const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
-    const uint32_t u0 = (uint32_t)f * frameUnits, u1 = u0 + frameUnits;
-    // the slots that deliver to this frame are the members of the teams whose units intersect the frame's: a contiguous
-    // run [sLo, sHi] (members without a band there deliver zeros).  Entry index = f - first frame of the slot's range: 0 for
-    // every team but the first, whose range may start in an earlier frame.
-    const uint32_t tLo = share_of_unit(p.geo, u0);
-    const uint32_t sLo = tLo * p.geo.group, sHi = (share_of_unit(p.geo, u1 - 1u) + 1u) * p.geo.group - 1u;
-    uint32_t eLo;
-    { uint32_t q0, q1; slot_units(p.geo, sLo, q0, q1); eLo = (uint32_t)f - q0 / frameUnits; }
-    double acc = 0.0;
-    constexpr int kBatch = 40;                          // one batch covers the 8 x 148 entries of a single frame
-    for (uint32_t sBase = sLo; sBase <= sHi; sBase += 32 * kBatch) {     // warp-uniform trip count (there are votes inside)
-        const uint32_t s0 = sBase + lane;
-        // One round = all of this lane's entries of the batch loaded at once (their L2 latencies overlap).  Normally the first
-        // round finds everything; otherwise polling rounds repeat until no entry is empty and the batch is loaded once more
-        // (values kept in registers across the polling loop cost MOVs in the 11-row body, of all places).
-        // Branch-free on purpose (lanes past the end re-read the last entry), and every decision is a VOTE.ALL predicate:
-        // with a per-lane branch in here, or a ballot/any deciding a loop exit, ptxas no longer proves the warp converged
-        // afterwards and wraps every branch of the 11-row body in BSSY/BSYNC (+10% instructions there).
-        unsigned long long v[kBatch];
-        bool missing = false;
-        #pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            const uint32_t s = s0 + 32u * k;
-            v[k] = 0ull;
-            if (s <= sHi) v[k] = entry_load(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u));
-        }
-        #pragma unroll
-        for (int k = 0; k < kBatch; ++k) missing |= (v[k] == kEmptyEntry);
-        if (!__all_sync(0xffffffffu, !missing)) {
-            bool allThere;
-            do {
-                unsigned miss = 0u;
-                #pragma unroll 20
-                for (int k = 0; k < kBatch; ++k) {
-                    const uint32_t s = min(s0 + 32u * k, sHi);
-                    miss |= (entry_load(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u)) == kEmptyEntry) ? 1u : 0u;
-                }
-                allThere = __all_sync(0xffffffffu, miss == 0u);
-            } while (!allThere);
-            #pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const uint32_t s = s0 + 32u * k;
-                v[k] = 0ull;
-                if (s <= sHi) v[k] = entry_load(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u));
-            }
-        }
-        #pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            const uint32_t s = s0 + 32u * k;
-            acc += __longlong_as_double((long long)v[k]);
-            if (s <= sHi) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p.partials + (size_t)s * p.entries + (s < sLo + p.geo.group ? eLo : 0u)), "l"(kEmptyEntry) : "memory");
-        }
+    // the slots that deliver to this frame are the members of the teams whose units intersect the frame's: a contiguous run
+    uint32_t expected = p.geo.slots;
+    if (p.frames != 1) {
+        const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
+        const uint32_t u0 = (uint32_t)f * frameUnits;
+        expected = (share_of_unit(p.geo, u0 + frameUnits - 1u) - share_of_unit(p.geo, u0) + 1u) * p.geo.group;
     }
-    acc = warp_sum(acc);
+    unsigned long long old = 0ull, mine = 0ull;
     if (lane == 0) {
+        mine = (1ull << kAccCountShift) | __double2ull_rn((v + p.accBias) * p.accScale);
+        old = atomicAdd(p.frameAcc + f, mine);
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    mine = __shfl_sync(0xffffffffu, mine, 0);
+    if (!__all_sync(0xffffffffu, (uint32_t)(old >> kAccCountShift) + 1u == expected)) return;     // not the last one (a vote: warp-uniform for ptxas)
+    const double acc = (double)((old + mine) & kAccSumMask) * p.accInvScale - (double)expected * p.accBias;
+    if (lane == 0) {
+        p.frameAcc[f] = 0ull;                           // ready for the next launch on this stream
         if (p.sums) p.sums[f] = acc;
         if (p.ssim) p.ssim[f] = (float)(acc * p.invCount);
     }
@@ -625,7 +579,6 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
     slot_units(p.geo, slot, q0, qEnd);
     if (q0 >= qEnd) return;
     const int fFirst = (int)(q0 / frameUnits), fLast = (int)((qEnd - 1u) / frameUnits);
-    double* myPart = p.partials + (size_t)slot * p.entries;
     int curFrame = fFirst;                                  // frames below this one have been delivered
     double total = 0.0;                                     // this lane's sum of curFrame's values so far
 
@@ -643,10 +596,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
             double v = warp_sum(total);
             #pragma unroll 1
             for (; curFrame < f; ++curFrame) {
-                if (lane == 0 && (uint32_t)(curFrame - fFirst) < p.entries) entry_store(myPart + (curFrame - fFirst), v);
-                // member 0 of the first team that touches the frame reduces it (the one call site of frame_reduce); for a single
-                // frame the host names the slot it expects to finish last, so that the reducer finds all entries at once
-                if (slot == (p.frames == 1 ? p.reducerSlot : share_of_unit(p.geo, (uint32_t)curFrame * frameUnits) * p.geo.group)) frame_reduce(p, x, curFrame, lane);
+                frame_deliver(p, x, curFrame, v, lane);     // (the one call site)
                 v = 0.0;
             }
             total = 0.0;

@@ -75,6 +75,7 @@ template <bool kU16> struct PixGeo {
 // a frame is ragged: its surplus members have nothing to do there (plan_slots keeps that waste small).
 constexpr int kPad = 2 * kHalo;
 constexpr int kDbgWords = 32;
+constexpr uint32_t kMaxSlots = 4095;     // the reduction counts the slots of a frame in 12 bits (see "reduction" in the kernel)
 
 struct SlotPlan {
     uint32_t slots;          // warp pairs that get work = teams * group
@@ -82,8 +83,6 @@ struct SlotPlan {
     uint32_t shareQ, shareR; // units per team: team j owns shareQ + (j < shareR) units
     uint32_t colUnits;       // units per column = outRows + pad
     uint32_t pad;            // padding units in front of every column: kPad, or more when the columns are cut into equal parts
-    uint32_t entries;        // partial-sum entries per slot = max number of frames whose units one slot can own
-    uint32_t reducerSlot;    // single frame: a slot that is expected to finish last (it adds up the partial sums)
 };
 constexpr uint32_t kCrossingUnits = 9;   // what it costs a team to start a second piece (its range crosses into the next column),
                                          // in row units: measured, the crossing teams of a 4K pair finish 3 us after the others
@@ -118,41 +117,24 @@ inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint
     plan->group = (uint32_t)group;
     plan->pad = kPad;
     plan->colUnits = (uint32_t)colUnits;
-    plan->reducerSlot = 0;
     // Few columns, many teams (a single image): cutting every column into k equal parts -- the column is padded up to
     // k * Q units -- leaves some teams idle but spares all others the second piece that a range crossing a column boundary
     // means.  Taken when it is the faster of the two by the model "time = units + start-up rows (+ a crossing)".
-    bool equalParts = false;
     if (cols > 1 && cols <= maxTeams) {
         unsigned long long k = maxTeams / cols;
         while (k > 1 && (colUnits + k - 1) / k < minUnits) --k;
         const unsigned long long partQ = (colUnits + k - 1) / k;
         const unsigned long long lineQ = (units + teams - 1) / teams;
         if (partQ >= minUnits && partQ < lineQ + kCrossingUnits && k * partQ * cols <= 0x7fffffffull) {
-            equalParts = true;
             teams = k * cols;
             plan->colUnits = (uint32_t)(k * partQ);
             plan->pad = (uint32_t)(k * partQ - outRows);
             units = cols * k * partQ;
-            if (k > 1) plan->reducerSlot = (uint32_t)group;             // the second team of the first column: a full part
         }
     }
     plan->slots = (uint32_t)(teams * group);
     plan->shareQ = (uint32_t)(units / teams);
     plan->shareR = (uint32_t)(units % teams);
-    if (!equalParts && frames == 1 && cols > 1) {
-        // the first team whose range crosses a column boundary and has output rows on both sides
-        for (unsigned long long t = 0; t < teams; ++t) {
-            const unsigned long long q0 = t * plan->shareQ + (t < plan->shareR ? t : plan->shareR), q1 = q0 + plan->shareQ + (t < plan->shareR ? 1 : 0);
-            const unsigned long long c1 = (q1 - 1) / colUnits;
-            if (q0 / colUnits != c1 && q1 - c1 * colUnits > (unsigned long long)kPad) { plan->reducerSlot = (uint32_t)(t * group); break; }
-        }
-    }
-    const unsigned long long frameUnits = groupsPerFrame * plan->colUnits;
-    // a range of n units touches at most (n + frameUnits - 2) / frameUnits + 1 frames
-    unsigned long long entries = ((unsigned long long)plan->shareQ + 1 + frameUnits - 2) / frameUnits + 1;
-    if (entries > frames) entries = frames;
-    plan->entries = (uint32_t)entries;
     return true;
 }
 
@@ -232,11 +214,10 @@ struct FusedParams {
     long long mapStep;       // floats between horizontally adjacent map values (1 = dense rows)
     int width, srcRows, outY0, outRows, frames;
     SlotGeo geo;
-    // reduction workspace (per stream): partial sums [slots][entries] (entry e of slot s belongs to frame
-    // e + the first frame whose units s owns); all ones ("empty") before the launch and again after it
-    double*   partials;
-    uint32_t  entries;
-    uint32_t  reducerSlot;   // frames == 1: the slot that adds the partial sums up (any slot; best one that finishes last)
+    // reduction workspace (per stream): one word per frame, zero before the launch and again after it: slot count in the
+    // high 12 bits, fixed-point sum of (slot sum + accBias) * accScale in the low 52 (see "reduction" in the kernel)
+    unsigned long long* frameAcc;
+    double accBias, accScale, accInvScale;
     double*   sums;          // out, may be NULL: [frames] sum of the SSIM values of each frame
     float*    ssim;          // out, may be NULL: [frames] float(sum * invCount)
     double    invCount;      // 1 / double(uint32(width*outRows))
