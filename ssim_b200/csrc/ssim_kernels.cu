@@ -91,25 +91,33 @@ template <int kByte>
 __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t magic) { return __uint_as_float(__byte_perm(word, magic, 0x7440 + kByte)); }
 
 // ------------------------------------------------------------------------------------------------ fused kernel
-// The kernel is PERSISTENT: the grid is at most kCtasPerSm x numSMs CTAs (all resident at once) and every warp pair owns
-// one SLOT of the work line (ssim_kernels.h, "work partition"): an equal share of the rows of all (frame, 64-column band)
+// The kernel is PERSISTENT: the grid is one CTA of 8 warp pairs per SM (all resident at once) and every warp pair owns one
+// SLOT of the work line (ssim_kernels.h, "work partition"): an equal share of the rows of all (frame, 64-column band)
 // columns, cut into pieces at column boundaries.  A pair walks through its pieces without ever leaving the kernel:
 //
-//   producer warp (warps 0-3)   TMA loads of 8-row pixel boxes into a 2-stage ring (running two blocks ahead, across piece
-//                               boundaries), clamp patching, u8/u16 -> f32, products, horizontal 11-tap pass; writes 8-row blocks of
-//                               {E_h[a'], E_h[b']}, {E_h[(a'-b')^2], E_h[a'b']} into a shared-memory ring of 3 (16-bit: 2) units
-//                               of 8 rows -- a unit is exactly one producer block, with a full/empty mbarrier each
-//   consumer warp (warps 4-7)   vertical 11-tap pass with eleven IN-PLACE accumulators per plane pair: its loop body is 11 rows,
-//                               fully unrolled, so accumulator slot s always owns the output rows == s (mod 11), every tap index
-//                               is static and nothing has to be shifted or renamed across iterations; the ring row it reads is
-//                               a warp-uniform running index; then the SSIM formula, map store and partial sums; the LAST
-//                               consumer warp of the grid to finish reduces the per-slot partial sums of every frame in a
-//                               fixed order and (strips across GPUs) exchanges the strip sums with the peers over NVLink
+//   producer warp (warps 0-7)   TMA loads of 8-row pixel boxes into a 2-stage ring (running two blocks ahead, across piece
+//                               boundaries), clamp patching, u8/u16 -> f32, products, horizontal 11-tap pass; writes 8-row blocks
+//                               of {E_h[a'], E_h[b']}, {E_h[(a'-b')^2], E_h[a'b']} into a shared-memory ring of two halves of 11
+//                               rows, a full/empty mbarrier each
+//   consumer warp (warps 8-15)  vertical 11-tap pass with eleven IN-PLACE accumulators per plane pair: its loop body is 11 rows
+//                               = one ring half, fully unrolled, so accumulator slot s always owns the output rows == s (mod 11),
+//                               every tap index and every ring offset is static and nothing has to be shifted or renamed across
+//                               iterations; then the SSIM formula, map store and partial sums; when the slot leaves a frame it
+//                               adds its sum to the frame's accumulator word with one atomic, and the slot whose atomic completes
+//                               the frame writes the result and (strips across GPUs) exchanges it with the peers over NVLink
 //
 // The two roles overlap in time (the consumer's dependent formula chain hides behind the producer's FMAs and vice versa),
 // setmaxnreg moves registers from the producers (96) to the consumers (160), and nothing is ever synchronised CTA-wide
-// after the prologue.  Every hand-over (TMA stage full/empty, ring unit full/empty) is an mbarrier on which each lane
+// after the prologue.  Every hand-over (TMA stage full/empty, ring half full/empty) is an mbarrier on which each lane
 // releases its own accesses and each lane acquires for itself: see the protocol table in DESIGN.md section 4.
+//
+// CODE LAYOUT MATTERS.  The two hot loops (consumer body ~1100 instructions, producer block loop ~750) together are ~30 KB
+// of code, and the instruction cache level behind the per-scheduler L0s holds 32 KB: when the address range from the
+// first instruction of the consumer body to the last of the producer loop exceeded it (36 KB, because the producer's
+// prologue and per-piece code sat between the two loops) 8% of all issue-slot samples were stall_no_instruction and the
+// kernel ran 9% slower (profiles/r02_code_layout.txt).  Hence: the first two pieces of a slot are looked up in the
+// kernel's common prologue, the producer's per-piece code sits BEHIND its block loop, cold paths inside the loops are
+// kept short, and tools/sass_summary.py reports the hot range.
 struct PieceGeo {           // everything warp-uniform
     int frame, bx, oy0, nOut, inY0;
     int nRows;              // input rows the vertical pass consumes: nOut + 10

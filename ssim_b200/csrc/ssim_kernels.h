@@ -40,9 +40,10 @@ constexpr int kBarsPerPair    = 8;                       // mbarriers per pair (
 
 // Per pixel type geometry of the TMA stage and the depth of the ring (everything after the widening is identical).
 //   8-bit : box rows of 96 bytes = 16 left margin + 64 columns + 16 right margin; a stage (8 rows of A, 8 rows of B) is 1536
-//           bytes; the ring holds 3 units of 8 rows.
+//           bytes.
 //   16-bit: box rows of 80 elements = 160 bytes (band column 0 again at byte 16, x coordinate bx-8 elements = 16 bytes
-//           aligned); a stage is 2560 bytes, the ring holds 2 units (3 would not leave room for 8 pairs per SM).
+//           aligned); a stage is 2560 bytes.
+// The ring (two halves of 11 rows) is the same for both.
 // Only the start of a box must be 128-byte aligned in shared memory (measured, tools/dev/tma_probe.cu): 8 x 96 = 768 and
 // 8 x 160 = 1280 both are multiples of 128, so A and B boxes follow each other without padding.
 template <bool kU16> struct PixGeo {
@@ -253,7 +254,7 @@ inline SlotGeo make_slot_geo(const SlotPlan& plan, uint32_t width)
 }
 
 // Cross-GPU sum fused into the kernel (strips of one image): every rank owns an exchange buffer of
-// 2 x kMaxRanks slots; the last consumer warp of rank r's kernel, after reducing the strip, stores the strip sum straight into
+// 2 x kMaxRanks slots; the consumer warp of rank r's kernel that completes the strip's sum stores it straight into
 // slot [epoch & 1][r] of EVERY peer's buffer (NVLink peer stores, value then epoch with release semantics at system scope), then
 // waits until its own buffer holds all `world` slots of this epoch and adds them up in rank order (deterministic, identical
 // on every rank).  world == 0: no exchange.

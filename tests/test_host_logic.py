@@ -173,3 +173,19 @@ def test_host_side_kernel_helpers(tmp_path, name):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and " ok" in r.stdout, r.stdout
+
+
+def test_hot_code_of_the_fused_kernel_fits_the_instruction_cache():
+    """The two hot loops of every variant of the fused kernel must stay within 32 KB of addresses ("code
+    layout"): beyond that the kernel loses ~9% to instruction fetch.  Checked on the built library with cuobjdump (no GPU)."""
+    import re
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_summary.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sizes = [float(x) for x in re.findall(r"hot code: .* = ([0-9.]+) KB", r.stdout)]
+    assert len(sizes) == 5, r.stdout                      # five instantiations of ssim_fused_kernel
+    assert max(sizes) < 32.0, sizes
+    assert r.stdout.count("no local-memory spills") >= 5, r.stdout       # and none of them spills
