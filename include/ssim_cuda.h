@@ -17,8 +17,9 @@
  *                                the reference has no device or batch notion; this is the entry the
  *                                bench and multi-GPU drivers use.
  *   ssim_cuda_compute_strips()   one large image split into row strips across several GPUs of one
- *                                process, partial sums combined with an NCCL all-reduce; replaces the
- *                                OpenMP tile distribution for gigapixel inputs (src/ssim-openmp.c:26-47)
+ *                                process, the per-GPU sums exchanged over NVLink peer memory inside the
+ *                                kernels (NCCL all-reduce on request); replaces the OpenMP tile
+ *                                distribution for gigapixel inputs (src/ssim-openmp.c:26-47)
  *
  * Return values: 0, EINVAL, ENOMEM, ENODEV (no usable device), EIO (CUDA/NCCL runtime failure; text in
  * ssim_cuda_last_error_string()).  All functions are thread-safe; a call never retains caller pointers.
@@ -104,8 +105,12 @@ int ssim_cuda_compute_device(int device, void* stream,
 /*
  * 16-bit pixels (dynamic range L = 65535: C1 = (0.01*65535)^2, C2 = (0.03*65535)^2), the extension the reference names but
  * does not implement (reference README.md:107-111; L is hard-wired to 255 at src/ssim.cpp:958, retrieve_tile reads bytes at
- * src/ssim.cpp:515-516).  Same kernel, same window, same border rule.  There is no reference implementation to compare
- * with: parity is pinned through the scale invariance SSIM_16(257*a, 257*b) == SSIM_8(a, b) and the 16-bit oracle.
+ * src/ssim.cpp:515-516).  Same kernel, same window, same border rule.  Parity is pinned against the reference's OWN
+ * template implementation: tests/ssim_naive.h instantiated as compute_ssim<double, uint16_t> (it takes its dynamic
+ * range from the pixel type) is compiled from the reference tree by oracle/Makefile (oracle/_ref/libnaive.so) and gates both
+ * the 16-bit oracle and the GPU path at |delta| <= 2e-6 global / 1e-3 per pixel (tests/test_oracle.py, tests/test_u16_gpu.py,
+ * committed vectors tests/golden/golden.json "u16_naive"); the scale invariance SSIM_16(257*a, 257*b) == SSIM_8(a, b) is a
+ * second, independent check.
  *
  * ssim_cuda_compute_u16():        like ssim_cuda_compute(); stepA/strideA/stepB/strideB are in uint16 ELEMENTS (signed).
  * ssim_cuda_compute_device_u16(): like ssim_cuda_compute_device(); pitches and frame strides in BYTES, multiples of 16.
@@ -127,8 +132,8 @@ int ssim_cuda_last_launch_count(void);
 
 /*
  * One host image pair split into horizontal strips (with 5 halo rows on interior edges) across
- * `nDevices` GPUs of this process.  The per-GPU double sums are combined INSIDE the kernels: the last warp of every
- * GPU's launch stores its strip sum into the peers' exchange buffers over NVLink and adds up what lands in its own
+ * `nDevices` GPUs of this process.  The per-GPU double sums are combined INSIDE the kernels: the warp that completes a
+ * GPU's strip sum stores it into the peers' exchange buffers over NVLink and adds up what lands in its own
  * (see ssim_cuda_compute_strip_allreduce below); SSIM_CUDA_STRIPS_NCCL=1 selects one ncclAllReduce of a double per GPU
  * instead.  Same argument meaning as ssim_cuda_compute(); pointers must be host pointers.
  */
@@ -139,9 +144,9 @@ int ssim_cuda_compute_strips(int nDevices, const int* devices, uint32_t width, u
                              float* ssim);
 
 /*
- * Strips of one image across GPUs with the cross-GPU sum fused into the reduction kernel: instead of an NCCL all-reduce after
- * the launch (ssim_cuda_compute_strips, or torch.distributed in a one-process-per-GPU driver), the reduction kernel of every
- * rank stores its strip sum straight into every peer's exchange buffer over NVLink (peer stores with release semantics at
+ * Strips of one image across GPUs with the cross-GPU sum fused into the kernel (the one launch per rank): instead of an NCCL
+ * all-reduce after the launch (torch.distributed in a one-process-per-GPU driver), the warp that completes the strip's sum on
+ * a rank stores it straight into every peer's exchange buffer over NVLink (peer stores with release semantics at
  * system scope), waits for the other ranks' sums to land in its own buffer and adds them in rank order: same result bits on
  * every rank, no host round trip, no collective launch.  Replaces the same reference code as ssim_cuda_compute_strips().
  *
