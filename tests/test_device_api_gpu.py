@@ -108,6 +108,33 @@ def test_many_frames_are_reduced_per_frame(shape):
             assert abs(float(dSsim[f]) - float(o)) <= GLOBAL_TOL, (f, rnd)
 
 
+@pytest.mark.parametrize("shape", [(1, 208, 77), (9, 208, 77), (1, 1920, 270), (70, 64, 40)])
+def test_negative_sums_survive_the_fixed_point_reduction(shape):
+    """The in-kernel reduction adds the slots' sums as biased fixed-point integers (one packed atomic per slot and frame):
+    anti-correlated images give NEGATIVE per-slot sums, which the bias must carry through; a second launch on the same
+    stream checks that the accumulator words were put back to zero."""
+    F, W, H = shape
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 256, (F, H, W), dtype=np.uint8)
+    b = (255 - a).astype(np.uint8)                    # local structure inverted: SSIM < 0 almost everywhere
+    b[F // 2] = a[F // 2]                             # ... and one frame that sums to exactly W*H
+    dA, dB = _dev(a), _dev(b)
+    dSums = torch.zeros(F, dtype=torch.float64, device="cuda")
+    dSsim = torch.zeros(F, dtype=torch.float32, device="cuda")
+    for rnd in range(2):
+        dSums.zero_(); dSsim.zero_()
+        api.compute_device(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, F, dA.data_ptr(), W, W * H, dB.data_ptr(), W, W * H,
+                           None, W, W * H, dSums.data_ptr(), dSsim.data_ptr())
+        torch.cuda.synchronize()
+        for f in sorted({0, F // 2, F - 1}):
+            o, tot, _ = oracle.oracle_ssim(a[f], b[f])
+            assert abs(float(dSsim[f]) - float(o)) <= GLOBAL_TOL, (f, rnd, float(dSsim[f]), float(o))
+            assert abs(float(dSums[f]) - tot) <= 2e-6 * W * H, (f, rnd)
+        assert float(dSums[F // 2]) == float(W * H)
+        if F > 1:
+            assert float(dSsim[0]) < -0.5
+
+
 def test_tuning_knobs_do_not_change_results():
     """ssim_cuda_set_tuning: any partition of the work (fewer warp pairs per SM, any minimum share) gives the same map values up
     to the per-piece centring (different pieces, same math)"""
