@@ -179,7 +179,7 @@ def exchange_open(device, handle):
 
 def compute_strip_allreduce(device, stream, width, src_rows, out_y0, out_rows, image_rows, d_a, pitch_a, d_b, pitch_b, d_map, map_pitch,
                             peer_bufs, rank, epoch, d_sum_all, d_ssim_all=None, d_status=None):
-    """ssim_cuda_compute_strip_allreduce(): one strip, sum over ranks exchanged through peer memory inside the reduction kernel."""
+    """ssim_cuda_compute_strip_allreduce(): one strip, sum over ranks exchanged through peer memory inside the (single) kernel launch."""
     arr = (C.c_void_p * len(peer_bufs))(*peer_bufs)
     _check(cuda_lib().ssim_cuda_compute_strip_allreduce(device, stream, width, src_rows, out_y0, out_rows, image_rows, d_a, pitch_a, d_b, pitch_b,
                                                        d_map, map_pitch, arr, len(peer_bufs), rank, epoch, d_sum_all, d_ssim_all, d_status))

@@ -1152,7 +1152,7 @@ int ssim_cuda_compute_device_u16(int device, void* stream, uint32_t width, uint3
                                (const uint8_t*)dB, pitchB, frameStrideB, dMap, mapPitch, mapFrameStride, dSums, dSsim, 2);
 }
 
-// ---- strip sums exchanged over peer memory (NVLink) inside the reduction kernel
+// ---- strip sums exchanged over peer memory (NVLink) inside the fused kernel
 int ssim_cuda_exchange_create(int device, void** dBuf, void* ipcHandle64)
 {
     if (!dBuf) return fail(EINVAL, "dBuf is NULL");

@@ -87,7 +87,7 @@ def test_short_strips_clamp_rows_like_the_reference(geom):
 @pytest.mark.parametrize("shape", [(37, 208, 77), (64, 64, 64), (130, 1280, 33), (300, 48, 20)])
 def test_many_frames_are_reduced_per_frame(shape):
     """More frames than warp pairs, frames smaller than a slot's share, slots spanning several frames: every frame's sum must
-    come out of the in-kernel per-frame reduction exactly once (and the arrival counters must be left clean for the next
+    come out of the in-kernel per-frame reduction exactly once (and the accumulator words must be left clean for the next
     launch, which the second round checks)."""
     F, W, H = shape
     a = np.stack([synth_pair(W, H, f)[0] for f in range(F)])
@@ -335,7 +335,7 @@ def test_full_size_known_answers(golden):
 
 
 def test_strip_sums_exchanged_through_peer_memory():
-    """ssim_cuda_compute_strip_allreduce(): the reduction kernel of every rank stores its strip sum into every peer's exchange
+    """ssim_cuda_compute_strip_allreduce(): the kernel of every rank stores its strip sum into every peer's exchange
     buffer and adds up what lands in its own.  One process drives all visible GPUs (ranks = devices; with a single GPU the
     ranks share device 0, which still exercises the slot / epoch protocol); every rank must end with the bits of the full-image
     result, twice in a row (epoch parity), and a missing peer must time out instead of hanging."""
