@@ -581,7 +581,7 @@ __device__ __forceinline__ void consumer_warp(const FusedParams& p, const Exchan
     const uint32_t col0Base = ringBase + vOff0, col1Base = ringBase + vOff1;
     uint32_t gbody = 0;
 
-    // partial sums: one entry per frame this slot's unit range touches, entry index = frame - first such frame
+    // the frames this slot's unit range touches: it delivers a sum to every one of them (0 where its units held no rows)
     const uint32_t frameUnits = p.geo.groupsPerFrame * p.geo.colUnits;
     uint32_t q0, qEnd;
     slot_units(p.geo, slot, q0, qEnd);
