@@ -189,6 +189,12 @@ void ssim_cuda_set_tuning(int maxPairsPerSm, int minSlotRows);
  */
 void ssim_cuda_debug_slot_times(unsigned long long* dTimes);
 
+/*
+ * Development aid for the tests: the entry (0..511) of the per-thread tensor-map descriptor cache that a plane with this base
+ * address and geometry uses.  Two planes of one call may share an entry; tests/test_device_api_gpu.py builds such a pair.
+ */
+int ssim_cuda_debug_map_cache_entry(const void* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch, int elemBytes);
+
 #ifdef __cplusplus
 }
 #endif

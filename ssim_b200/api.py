@@ -82,6 +82,8 @@ def cuda_lib():
     lib.ssim_cuda_set_tuning.restype = None
     lib.ssim_cuda_debug_slot_times.argtypes = [C.c_void_p]
     lib.ssim_cuda_debug_slot_times.restype = None
+    lib.ssim_cuda_debug_map_cache_entry.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int]
+    lib.ssim_cuda_debug_map_cache_entry.restype = C.c_int
     lib._bound = True
     return lib
 

@@ -184,22 +184,29 @@ struct MapCache {
 };
 thread_local std::unique_ptr<MapCache> g_mapCache;
 
-int get_plane_map(const CUtensorMap** out, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
+int map_cache_entry(const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch, int elemBytes)
+{
+    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+    h ^= ((uint64_t)width << 32 | rows) * 0xC2B2AE3D27D4EB4Full;
+    h ^= (uint64_t)pitch * 0x165667B19E3779F9ull + frames + (uint64_t)elemBytes * 131;
+    return (int)((h >> 40) % MapCache::kEntries);
+}
+
+// The descriptor is COPIED out (128 bytes): a call looks up two planes, and when both hash to the same entry the second
+// look-up replaces the first one's descriptor -- a pointer into the cache would then describe the wrong image.
+int get_plane_map(CUtensorMap* out, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
                   size_t frameStride, int elemBytes)
 {
     if (!g_mapCache) g_mapCache.reset(new MapCache());
     MapCache& mc = *g_mapCache;
     const MapKey k = {base, pitch, frames > 1 ? frameStride : 0, width, rows, frames, elemBytes};
-    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
-    h ^= ((uint64_t)width << 32 | rows) * 0xC2B2AE3D27D4EB4Full;
-    h ^= (uint64_t)pitch * 0x165667B19E3779F9ull + frames + (uint64_t)elemBytes * 131;
-    const int slot = (int)((h >> 40) % MapCache::kEntries);
-    if (mc.key[slot] == k && k.base != nullptr) { *out = &mc.tm[slot]; return 0; }
+    const int slot = map_cache_entry(base, width, rows, frames, pitch, elemBytes);
+    if (mc.key[slot] == k && k.base != nullptr) { *out = mc.tm[slot]; return 0; }
     mc.key[slot].base = nullptr;
     int rc = make_plane_map(&mc.tm[slot], base, width, rows, frames, pitch, frameStride, elemBytes);
     if (rc) return rc;
     mc.key[slot] = k;
-    *out = &mc.tm[slot];
+    *out = mc.tm[slot];
     return 0;
 }
 
@@ -431,7 +438,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     WorkspaceView ws;
     int rc = get_workspace(c, stream, frames, &ws);
     if (rc) return rc;
-    const CUtensorMap *tmA, *tmB;
+    alignas(64) CUtensorMap tmA, tmB;
     if ((rc = get_plane_map(&tmA, dA, width, srcRows, frames, pitchA, frameStrideA, elemBytes))) return rc;
     if ((rc = get_plane_map(&tmB, dB, width, srcRows, frames, pitchB, frameStrideB, elemBytes))) return rc;
 
@@ -463,7 +470,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     }
     p.eps2 = c->eps2;
     p.dbgTimes = g_dbgTimes.load(std::memory_order_relaxed);
-    CU_TRY(ssimk::launch_fused(stream, *tmA, *tmB, p, xchg));      // the ONLY launch: reduction (and exchange) happen inside
+    CU_TRY(ssimk::launch_fused(stream, tmA, tmB, p, xchg));      // the ONLY launch: reduction (and exchange) happen inside
     g_lastLaunches = 1;
     return 0;
 }
@@ -1250,6 +1257,11 @@ int ssim_cuda_synth_fill(int device, void* stream, uint8_t* dA, size_t pitchA, u
 }
 
 void ssim_cuda_debug_slot_times(unsigned long long* dTimes) { g_dbgTimes.store(dTimes, std::memory_order_relaxed); }
+
+int ssim_cuda_debug_map_cache_entry(const void* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch, int elemBytes)
+{
+    return map_cache_entry((const uint8_t*)base, width, rows, frames, pitch, elemBytes);
+}
 
 void ssim_cuda_set_tuning(int maxPairsPerSm, int minSlotRows)
 {

@@ -334,6 +334,65 @@ def test_full_size_known_answers(golden):
         assert abs(float(fv[i].item()) - golden["synthetic"]["1920x1080_f%d" % f]["ref_f64_auto"]) <= GLOBAL_TOL
 
 
+def test_two_planes_sharing_a_descriptor_cache_entry():
+    """The tensor-map descriptors of a call come from a direct-mapped per-thread cache; A and B of one call may fall into the
+    same entry (1 call in 512 with unrelated addresses).  Build such a pair on purpose: the second look-up must not change what
+    the first one returned (a round-2 bug handed out pointers into the cache: the call then compared B with B, SSIM = 1)."""
+    lib = api.cuda_lib()
+    W, H = 208, 77
+    plane = W * H                                         # 16016 bytes: a multiple of 16
+    n = 4096
+    pool = torch.empty(n * plane, dtype=torch.uint8, device="cuda")
+    seen = {}
+    pair = None
+    for i in range(n):
+        e = lib.ssim_cuda_debug_map_cache_entry(pool.data_ptr() + i * plane, W, H, 1, W, 1)
+        if e in seen:
+            pair = (seen[e], i)
+            break
+        seen[e] = i
+    assert pair is not None
+    a, b = synth_pair(W, H, 3)
+    pool[pair[0] * plane:(pair[0] + 1) * plane] = _dev(a).flatten()
+    pool[pair[1] * plane:(pair[1] + 1) * plane] = _dev(b).flatten()
+    val = torch.zeros(1, dtype=torch.float32, device="cuda")
+    want = float(oracle.oracle_ssim(a, b)[0])
+    for _ in range(2):                                    # cold entry, then whatever the first call left in it
+        api.compute_device(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, 1, pool.data_ptr() + pair[0] * plane, W, 0,
+                           pool.data_ptr() + pair[1] * plane, W, 0, None, 0, 0, None, val.data_ptr())
+        torch.cuda.synchronize()
+        assert abs(float(val.item()) - want) <= GLOBAL_TOL, (float(val.item()), want)
+
+
+def test_full_size_properties_4k():
+    """Size-independent properties at the headline size (3840x2160, BASELINE.json configs[2]): SSIM(a, b) == SSIM(b, a) bit for
+    bit, map included (the kernel's formula is symmetric in its two inputs); the global sum is the sum of the stored map; a
+    frame scores the same alone and as any member of a batch (other partition, other centring pixels: to 2e-7)."""
+    st = torch.cuda.current_stream().cuda_stream
+    W, H, F = 3840, 2160, 3
+    a = torch.empty((F, H, W), dtype=torch.uint8, device="cuda")
+    b = torch.empty_like(a)
+    for f in range(F):
+        api.synth_fill(0, st, a[f].data_ptr(), W, b[f].data_ptr(), W, W, H, 0, 5)        # three copies of frame 5
+    m1 = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    m2 = torch.empty_like(m1)
+    s1 = torch.empty(1, dtype=torch.float64, device="cuda"); s2 = torch.empty_like(s1)
+    v1 = torch.empty(1, dtype=torch.float32, device="cuda"); v2 = torch.empty_like(v1)
+    api.compute_device(0, st, W, H, 0, H, 1, a.data_ptr(), W, 0, b.data_ptr(), W, 0, m1.data_ptr(), W, 0, s1.data_ptr(), v1.data_ptr())
+    api.compute_device(0, st, W, H, 0, H, 1, b.data_ptr(), W, 0, a.data_ptr(), W, 0, m2.data_ptr(), W, 0, s2.data_ptr(), v2.data_ptr())
+    torch.cuda.synchronize()
+    assert float(v1.item()) == float(v2.item()) and float(s1.item()) == float(s2.item())
+    assert torch.equal(m1, m2)
+    assert abs(float(m1.double().sum().item()) - float(s1.item())) <= 1e-7 * W * H
+    vb = torch.empty(F, dtype=torch.float32, device="cuda")
+    sb = torch.empty(F, dtype=torch.float64, device="cuda")
+    api.compute_device(0, st, W, H, 0, H, F, a.data_ptr(), W, W * H, b.data_ptr(), W, W * H, None, 0, 0, sb.data_ptr(), vb.data_ptr())
+    torch.cuda.synchronize()
+    for f in range(F):
+        assert abs(float(vb[f].item()) - float(v1.item())) <= 2e-7, f
+        assert abs(float(sb[f].item()) - float(s1.item())) <= 2e-7 * W * H, f
+
+
 def test_strip_sums_exchanged_through_peer_memory():
     """ssim_cuda_compute_strip_allreduce(): the kernel of every rank stores its strip sum into every peer's exchange
     buffer and adds up what lands in its own.  One process drives all visible GPUs (ranks = devices; with a single GPU the
