@@ -139,14 +139,21 @@ __device__ __forceinline__ void piece_geo(const FusedParams& p, const Piece& pc,
 // E[x^2] - mu^2 small even on flat regions (DESIGN.md "Numerics").  Any integer works; both warps of a pair must of course
 // use the same one.
 template <bool kU16>
-__device__ __forceinline__ void piece_centre(const FusedParams& p, const PieceGeo& g, float& ca, float& cb)
+__device__ __forceinline__ void piece_centre_raw(const FusedParams& p, const PieceGeo& g, unsigned& ra, unsigned& rb)
 {
     const int cx = min(g.bx + kBandW / 2, p.width - 1);
     const int cy = min(max(g.oy0, 0), p.srcRows - 1);
     const uint8_t* pa = p.a + (long long)g.frame * p.frameStrideA + (long long)cy * p.pitchA;
     const uint8_t* pb = p.b + (long long)g.frame * p.frameStrideB + (long long)cy * p.pitchB;
-    if (kU16) { ca = (float)__ldg((const uint16_t*)pa + cx); cb = (float)__ldg((const uint16_t*)pb + cx); }
-    else      { ca = (float)__ldg(pa + cx);                  cb = (float)__ldg(pb + cx); }
+    if (kU16) { ra = __ldg((const uint16_t*)pa + cx); rb = __ldg((const uint16_t*)pb + cx); }
+    else      { ra = __ldg(pa + cx);                  rb = __ldg(pb + cx); }
+}
+template <bool kU16>
+__device__ __forceinline__ void piece_centre(const FusedParams& p, const PieceGeo& g, float& ca, float& cb)
+{
+    unsigned ra, rb;
+    piece_centre_raw<kU16>(p, g, ra, rb);
+    ca = (float)ra; cb = (float)rb;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -181,8 +188,8 @@ constexpr uint32_t kBarTmaFull = 0, kBarStageEmpty = 16, kBarRingFull = 32, kBar
 // ---- producer: TMA + horizontal pass
 template <bool kU16>
 __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUtensorMap* tmB, const FusedParams& p, int lane,
-                                              uint32_t pairSmem, uint32_t barBase, PieceCursor cur, const PieceGeo& g0, float ca0, float cb0,
-                                              bool have1, const PieceGeo& g1, float ca1, float cb1)
+                                              uint32_t pairSmem, uint32_t barBase, PieceCursor cur, const PieceGeo& g0, unsigned ra0, unsigned rb0,
+                                              bool have1, const PieceGeo& g1, unsigned ra1, unsigned rb1)
 {
     typedef PixGeo<kU16> G;
     constexpr int kBoxW = G::kBoxBytes, kImgStageBytes = G::kImgStageBytes, kStageBytes = G::kStageBytes;
@@ -219,10 +226,15 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
         }
     };
     PieceGeo g = g0, gN = g1;                               // the slot's first two pieces: found by the kernel's common prologue
-    float ca = ca0, cb = cb0, caN = ca1, cbN = cb1;
     bool haveN = have1;
     #pragma unroll 1
     for (int b = 0; b < kStages; ++b) issue(g, b, (uint32_t)b, false, 0, false);
+    // the centring pixels were loaded by the common prologue and are first touched HERE, after the first TMA boxes are on
+    // their way (converting them there put a DRAM round trip in front of the first TMA issue of every launch)
+    // (volatile: keeps the conversions, i.e. the wait for the loads, behind the TMA issue above)
+    float ca, cb, caN, cbN;
+    asm volatile("cvt.rn.f32.u32 %0, %4;\n\tcvt.rn.f32.u32 %1, %5;\n\tcvt.rn.f32.u32 %2, %6;\n\tcvt.rn.f32.u32 %3, %7;"
+                 : "=f"(ca), "=f"(cb), "=f"(caN), "=f"(cbN) : "r"(ra0), "r"(rb0), "r"(ra1), "r"(rb1));
 
     const uint32_t magic = p.magic;                    // 0x4B000000, passed as a parameter so that it lives in a register and
                                                        // PRMT takes the byte selector as its immediate (no per-PRMT selector MOV)
@@ -711,21 +723,22 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // the samples against 2% when the two hot loops are nearly adjacent).  The empty volatile asm pins the values here.
     PieceCursor cur0;
     PieceGeo g0 = PieceGeo(), g1 = PieceGeo();
-    float ca0 = 0.f, cb0 = 0.f, ca1 = 0.f, cb1 = 0.f;
+    unsigned ra0 = 0, rb0 = 0, ra1 = 0, rb1 = 0;          // centring pixels of the two pieces, as loaded
     int have0 = 0, have1 = 0;
     if (slot < p.geo.slots) {
         cursor_init(cur0, p.geo, slot);
         Piece pc;
         have0 = cursor_next(cur0, p.geo, pc) ? 1 : 0;
-        if (have0) { piece_geo(p, pc, g0); piece_centre<kU16>(p, g0, ca0, cb0); }
+        if (have0) { piece_geo(p, pc, g0); piece_centre_raw<kU16>(p, g0, ra0, rb0); }
         have1 = have0 && cursor_next(cur0, p.geo, pc) ? 1 : 0;
-        if (have1) { piece_geo(p, pc, g1); piece_centre<kU16>(p, g1, ca1, cb1); }
+        if (have1) { piece_geo(p, pc, g1); piece_centre_raw<kU16>(p, g1, ra1, rb1); }
     } else {
         cur0.q = cur0.qEnd = cur0.colBase = 0; cur0.frame = cur0.band = 0;
     }
     asm volatile("" : "+r"(cur0.q), "+r"(cur0.qEnd), "+r"(cur0.colBase), "+r"(cur0.frame), "+r"(cur0.band), "+r"(have0), "+r"(have1));
-    asm volatile("" : "+r"(g0.frame), "+r"(g0.bx), "+r"(g0.oy0), "+r"(g0.nOut), "+r"(g0.inY0), "+r"(g0.nRows), "+r"(g0.nBlk), "+f"(ca0), "+f"(cb0));
-    asm volatile("" : "+r"(g1.frame), "+r"(g1.bx), "+r"(g1.oy0), "+r"(g1.nOut), "+r"(g1.inY0), "+r"(g1.nRows), "+r"(g1.nBlk), "+f"(ca1), "+f"(cb1));
+    // (the centring pixels are NOT pinned and not converted here: their loads stay in flight across the role branch)
+    asm volatile("" : "+r"(g0.frame), "+r"(g0.bx), "+r"(g0.oy0), "+r"(g0.nOut), "+r"(g0.inY0), "+r"(g0.nRows), "+r"(g0.nBlk));
+    asm volatile("" : "+r"(g1.frame), "+r"(g1.bx), "+r"(g1.oy0), "+r"(g1.nOut), "+r"(g1.inY0), "+r"(g1.nRows), "+r"(g1.nBlk));
 
     if (isConsumer) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kConsumerRegs));
@@ -734,7 +747,7 @@ ssim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kProducerRegs));
         if (slot >= p.geo.slots || !have0) return;          // a slot without any output row
-        producer_warp<kU16>(&tmA, &tmB, p, lane, pairSmem, barBase, cur0, g0, ca0, cb0, have1 != 0, g1, ca1, cb1);
+        producer_warp<kU16>(&tmA, &tmB, p, lane, pairSmem, barBase, cur0, g0, ra0, rb0, have1 != 0, g1, ra1, rb1);
     }
 }
 
