@@ -148,6 +148,20 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
+CUtensorMapL2promotion l2_promotion()
+{
+    static const CUtensorMapL2promotion promo = [] {
+        // 64 bytes: a box row (96 bytes starting 16 bytes left of a 64-byte aligned band) then pulls exactly the 64-byte granules
+        // it touches.  Measured on 64 x 4K (profiles/r02_l2_promotion.txt): DRAM reads 1.39 GB with 64 B, 1.71 GB with 128 B
+        // (the 16-byte margins at a team's edges each cost a whole 128-byte line) and with NONE, 1.85 GB with 256 B;
+        // algorithmic 1.06 GB; same kernel time in all four.  SSIM_CUDA_L2_PROMOTION = 0 / 64 / 128 / 256 overrides it.
+        const char* e = getenv("SSIM_CUDA_L2_PROMOTION");
+        const int v = e ? atoi(e) : 64;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
+    return promo;
+}
+
 int make_plane_map(CUtensorMap* tm, const uint8_t* base, uint32_t width, uint32_t rows, uint32_t frames, size_t pitch,
                    size_t frameStride, int elemBytes)
 {
@@ -158,7 +172,7 @@ int make_plane_map(CUtensorMap* tm, const uint8_t* base, uint32_t width, uint32_
     const cuuint32_t box[3]     = {(cuuint32_t)(elemBytes == 2 ? ssimk::PixGeo<true>::kBoxElems : ssimk::PixGeo<false>::kBoxElems), (cuuint32_t)ssimk::kLoadRows, 1};
     const cuuint32_t estr[3]    = {1, 1, 1};
     CUresult r = enc(tm, elemBytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EIO, "cuTensorMapEncodeTiled failed (%d) for %ux%ux%u pitch %zu", (int)r, width, rows, frames, pitch);
     return 0;
