@@ -146,7 +146,7 @@ int ssim_cuda_compute_strips(int nDevices, const int* devices, uint32_t width, u
 /*
  * Strips of one image across GPUs with the cross-GPU sum fused into the kernel (the one launch per rank): instead of an NCCL
  * all-reduce after the launch (torch.distributed in a one-process-per-GPU driver), the warp that completes the strip's sum on
- * a rank stores it straight into every peer's exchange buffer over NVLink (peer stores with release semantics at
+ * a rank stores it straight into every peer's exchange buffer over NVLink (relaxed peer stores of self-validating words at
  * system scope), waits for the other ranks' sums to land in its own buffer and adds them in rank order: same result bits on
  * every rank, no host round trip, no collective launch.  Replaces the same reference code as ssim_cuda_compute_strips().
  *

@@ -470,25 +470,30 @@ __device__ __forceinline__ void frame_deliver(const FusedParams& p, const Exchan
         if (p.ssim) p.ssim[f] = (float)(acc * p.invCount);
     }
     if (x.world > 0) {
-        // strip sums of all ranks (frames == 1): one lane per peer stores value then epoch (release, system scope) into the
-        // peer's buffer, then waits for the peer's slot of this epoch in its own buffer; the sum runs in rank order on every rank
+        // strip sums of all ranks (frames == 1): one lane per peer stores the sum into the peer's buffer as two 64-bit words,
+        // each carrying 32 bits of the double under a 32-bit epoch tag, then waits until both words of the peer's slot in its
+        // own buffer carry this epoch; the sum runs in rank order on every rank.  Every word validates itself, so the stores
+        // and loads are relaxed: no release / acquire at system scope (the release used to wait for this lane's map stores).
         const unsigned half = (unsigned)(x.epoch & 1ull) * kMaxRanks;
+        const unsigned long long tag = ((x.epoch % 0xffffffffull) + 1ull) << 32;         // never 0: fresh buffers are zero
         double val = 0.0;
         int failed = 0;
         if (lane < x.world) {
             ExchangeSlot* dst = x.peers[lane] + half + x.rank;
-            dst->value = acc;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(&dst->epoch), "l"(x.epoch) : "memory");
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(acc);
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&dst->lo), "l"(tag | (bits & 0xffffffffull)) : "memory");
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(&dst->hi), "l"(tag | (bits >> 32)) : "memory");
             const ExchangeSlot* src = x.peers[x.rank] + half + lane;
-            unsigned long long t0, now, seen;
+            unsigned long long t0, now, lo, hi;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
             for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&src->epoch) : "memory");
-                if (seen == x.epoch) break;
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(lo) : "l"(&src->lo) : "memory");
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(hi) : "l"(&src->hi) : "memory");
+                if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (now - t0 > x.timeoutNs) { failed = 1; break; }
             }
-            val = *(volatile const double*)&src->value;
+            val = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
         }
         failed = __any_sync(0xffffffffu, failed);
         double total = 0.0;

@@ -255,11 +255,11 @@ inline SlotGeo make_slot_geo(const SlotPlan& plan, uint32_t width)
 
 // Cross-GPU sum fused into the kernel (strips of one image): every rank owns an exchange buffer of
 // 2 x kMaxRanks slots; the consumer warp of rank r's kernel that completes the strip's sum stores it straight into
-// slot [epoch & 1][r] of EVERY peer's buffer (NVLink peer stores, value then epoch with release semantics at system scope), then
+// slot [epoch & 1][r] of EVERY peer's buffer (NVLink peer stores: two 64-bit words, each 32 bits of the sum under a 32-bit epoch tag, so no ordering is needed), then
 // waits until its own buffer holds all `world` slots of this epoch and adds them up in rank order (deterministic, identical
 // on every rank).  world == 0: no exchange.
 constexpr int kMaxRanks = 16;
-struct ExchangeSlot { double value; unsigned long long epoch; };
+struct ExchangeSlot { unsigned long long lo, hi; };   // (epoch tag << 32) | low / high 32 bits of the double: each word validates itself
 struct ExchangeParams {
     ExchangeSlot* peers[kMaxRanks];   // device pointers to every rank's exchange buffer (own one at [rank])
     int world, rank;
