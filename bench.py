@@ -160,6 +160,21 @@ def config(args, n):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def host_threads_for_reference():
+    """The reference arm gets ALL host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank, which
+    would silently run the reference's OpenMP pool on one thread: the OpenMP runtime the reference library is linked with
+    (libgomp) is told explicitly, and what it then reports is what goes into `cores`."""
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    want = max(1, min(want, 64))                  # the reference caps its pool at 64 threads (src/ssim.cpp:1025-1029)
+    try:
+        gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+        gomp.omp_set_num_threads(C.c_int(want))
+        gomp.omp_get_max_threads.restype = C.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return want
+
+
 def time_reference(frames_host, seconds=None, steps=None, warmup=1):
     """Runs the unmodified reference (oracle/_ref/libref_f32.so, rmgr_ssim_compute_ssim_openmp) on host frames.
     Either for ~`seconds` of wall clock or for `steps` timed steps of len(frames_host) frames each."""
@@ -169,7 +184,7 @@ def time_reference(frames_host, seconds=None, steps=None, warmup=1):
     from ssim_b200._abi import make_params
     lib = oracle.ref_lib("f32")
     lib.ref_select_impl(oracle.IMPL_AUTO)
-    cores = min(os.cpu_count() or 1, 64)          # reference caps threads at 64 (src/ssim.cpp:1025-1029)
+    cores = host_threads_for_reference()
     m = np.empty((H, W), dtype=np.float32)
     out = C.c_float()
 
