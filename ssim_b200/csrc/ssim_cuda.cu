@@ -466,14 +466,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.geo = ssimk::make_slot_geo(plan, width);
     p.frameAcc = ws.frameAcc;
-    {
-        // fixed-point format of the in-kernel reduction (see "reduction" in ssim_kernels.cu): every slot adds (its sum + bias)
-        // * 2^k to the 52-bit field of its frame; bias >= the pixels a slot can hold of one frame, k as large as fits
-        const double bias = ((double)plan.shareQ + 1.0) * ssimk::kBandW;
-        int k = 0;
-        while (k < 40 && (double)plan.slots * 2.0 * bias * std::ldexp(1.0, k + 2) < 4503599627370496.0) ++k;      // 2^52
-        p.accBias = bias; p.accScale = std::ldexp(1.0, k); p.accInvScale = std::ldexp(1.0, -k);
-    }
+    ssimk::acc_format(plan, &p.accBias, &p.accScale, &p.accInvScale);
     p.sums = dSums; p.ssim = dSsim;
     p.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];

@@ -424,7 +424,7 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
 // (and, up to the rounding of each slot's sum to the fixed-point grid, independent of how the work was partitioned).
 // bias: SSIM values may be negative (> -1); every slot adds p.accBias >= its number of pixels so that what goes into the
 // field is non-negative, and the finisher takes expected * bias off again.  Scale: p.accScale = 2^k with k chosen by the
-// host so that the field cannot overflow 52 bits (4K frame: k = 27, i.e. 7e-9 per slot; the rounding of all slots together
+// host (acc_format() in ssim_kernels.h) so that the field cannot overflow (one 4K frame: k = 25, i.e. 1.5e-8 per slot; the rounding of all slots together
 // moves the mean SSIM of a 4K frame by < 1e-12).
 // (Protocols tried before: partial sums in memory + fence + atomic counter + the last arriver adds them up: 4.5 us behind
 // the last row of a single image -- the fence waits for the slot's map stores, then the atomic's round trip, then 1184

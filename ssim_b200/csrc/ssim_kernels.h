@@ -139,6 +139,19 @@ inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint
     return true;
 }
 
+// Fixed-point format of the in-kernel reduction (see "reduction" in ssim_kernels.cu): every slot adds (its sum of a frame +
+// bias) * scale to the 52-bit field of the frame's accumulator word.  bias >= the pixels a slot can hold of one frame (a slot's
+// units there x 64 columns; SSIM > -1, so sum + bias >= 0); scale = 2^k, k <= 40 as large as keeps slots * 2 * bias * scale below
+// 2^50.  Pure host logic, checked in tests/clients/plan_check.cpp.
+inline void acc_format(const SlotPlan& plan, double* bias, double* scale, double* invScale)
+{
+    const double b = ((double)plan.shareQ + 1.0) * (double)kBandW;
+    double s = 1.0;
+    int k = 0;
+    while (k < 40 && (double)plan.slots * 2.0 * b * (s * 2.0) * 4.0 < 4503599627370496.0) { s *= 2.0; ++k; }     // 2^52
+    *bias = b; *scale = s; *invScale = 1.0 / s;
+}
+
 // One piece: rows [r0, r0 + nOut) of one band of one frame (relative to the first output row of the call).
 struct Piece {
     int frame, band;

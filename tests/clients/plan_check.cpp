@@ -30,6 +30,14 @@ static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_
     expect(plan.pad == 10 || (plan.shareR == 0 && plan.colUnits % plan.shareQ == 0), "padded columns are cut into equal parts", w, h, f, plan.slots);
     expect((uint64_t)g.groupsPerFrame * plan.group >= bands && (uint64_t)(g.groupsPerFrame - 1) * plan.group < bands, "groups cover the bands", w, h, f, plan.slots);
     expect((double)bands / ((double)g.groupsPerFrame * plan.group) >= 0.9 || bands < 8, "little ragged waste", w, h, f, plan.slots);
+    {
+        double bias, scale, inv;
+        ssimk::acc_format(plan, &bias, &scale, &inv);
+        expect(bias >= ((double)plan.shareQ + 1.0) * 64.0, "reduction bias covers a slot's pixels of one frame", w, h, f, plan.slots);
+        expect(scale >= 1.0 && scale * inv == 1.0 && scale <= 1099511627776.0, "reduction scale is a power of two in [1, 2^40]", w, h, f, plan.slots);
+        expect((double)plan.slots * 2.0 * bias * scale < 1125899906842624.0, "all slots of a frame together stay below 2^50 in the 52-bit field", w, h, f, plan.slots);
+        expect(plan.slots <= ssimk::kMaxSlots, "slot count fits the 12-bit arrival counter", w, h, f, plan.slots);
+    }
     std::vector<uint32_t> nextRow(cols, 0);          // rows [0, nextRow) of each column are covered so far
     uint64_t lastCol = 0;
     bool first = true;
