@@ -404,6 +404,11 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
         }
         firstHalf += ((uint32_t)g.nRows + kTaps - 1) / kTaps;
         if (!haveN) break;
+        // The last block of a piece may have put filler rows into the half after the piece's last one, which is the next
+        // piece's first half: other lanes of this warp are about to overwrite them.  Same warp, program order -- but two
+        // lanes writing one address need a warp-level sync in between to be ordered (compute-sanitizer racecheck reports the
+        // pair otherwise).
+        __syncwarp();
         // the piece fetched one ahead becomes the current one; fetch the next.  (This code sits BEHIND the block loop in the
         // binary; its first two executions were moved into the kernel's common prologue so that no cold code lies between the
         // consumer's body and the block loop.)
