@@ -15,3 +15,15 @@ lib.ssim_cuda_set_tuning(4, 0)           # fewer warp pairs per SM than the defa
 a, b = synth_pair(640, 720, 5)
 print("4 pairs per SM", api.compute_ssim(a, b, want_map=True)[0])
 lib.ssim_cuda_set_tuning(0, 0)
+# slots that walk through several pieces (many small frames in one launch) and the in-kernel per-frame reduction
+import torch
+F, W, H = 70, 208, 77
+fa = torch.from_numpy(np.stack([synth_pair(W, H, f)[0] for f in range(F)])).cuda()
+fb = torch.from_numpy(np.stack([synth_pair(W, H, f)[1] for f in range(F)])).cuda()
+fm = torch.empty((F, H, W), dtype=torch.float32, device="cuda")
+fs = torch.empty(F, dtype=torch.float32, device="cuda")
+for _ in range(2):
+    api.compute_device(0, torch.cuda.current_stream().cuda_stream, W, H, 0, H, F, fa.data_ptr(), W, W * H, fb.data_ptr(), W, W * H,
+                       fm.data_ptr(), W, W * H, None, fs.data_ptr())
+torch.cuda.synchronize()
+print("70 frames in one launch", float(fs[0]), float(fs[F - 1]))
