@@ -334,6 +334,38 @@ def test_full_size_known_answers(golden):
         assert abs(float(fv[i].item()) - golden["synthetic"]["1920x1080_f%d" % f]["ref_f64_auto"]) <= GLOBAL_TOL
 
 
+def test_calls_can_be_captured_into_a_cuda_graph():
+    """ssim_cuda_compute_device() only enqueues work on the caller's stream (one kernel launch; workspace and descriptors are
+    in place after the first call on that stream), so a sequence of calls can be captured into a CUDA graph and replayed."""
+    W, H, n = 640, 360, 4
+    pairs = [synth_pair(W, H, f) for f in range(n)]
+    dA = [_dev(p[0]) for p in pairs]
+    dB = [_dev(p[1]) for p in pairs]
+    val = torch.zeros(n, dtype=torch.float32, device="cuda")
+    maps = torch.zeros((n, H, W), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+
+    def enqueue():
+        for i in range(n):
+            api.compute_device(0, s.cuda_stream, W, H, 0, H, 1, dA[i].data_ptr(), W, 0, dB[i].data_ptr(), W, 0,
+                               maps[i].data_ptr(), W, 0, None, val[i:].data_ptr())
+
+    enqueue()                                             # first use of the stream: allocates its workspace
+    torch.cuda.synchronize()
+    want = val.clone(); want_maps = maps.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        enqueue()
+    for _ in range(2):
+        val.zero_(); maps.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(val, want) and torch.equal(maps, want_maps)
+    for i in range(n):
+        assert abs(float(val[i]) - float(oracle.oracle_ssim(*pairs[i])[0])) <= GLOBAL_TOL
+
+
 def test_two_planes_sharing_a_descriptor_cache_entry():
     """The tensor-map descriptors of a call come from a direct-mapped per-thread cache; A and B of one call may fall into the
     same entry (1 call in 512 with unrelated addresses).  Build such a pair on purpose: the second look-up must not change what
