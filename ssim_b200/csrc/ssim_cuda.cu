@@ -387,7 +387,7 @@ int acquire_host_context(Context** c, std::unique_lock<std::mutex>* lock)
 // See "work partition" in ssim_kernels.h: the persistent grid's warp pairs ("slots") share the rows of all (frame, band)
 // columns evenly.  The only choices left to the host are how many CTAs per SM to use and how thin the work may be spread
 // (a slot pays 10 start-up rows, so tiny inputs use fewer slots).
-const uint32_t kDefaultMinSlotRows = 12;
+const uint32_t kDefaultMinSlotRows = 6;       // measured (tools/dev/minrows_sweep.py): 256x256 9.5 us with 4-6, 11.0 with 12, 13.5 with 16; large inputs do not care
 
 bool plan_for(const Context* c, uint32_t width, uint32_t outRows, uint32_t frames, ssimk::SlotPlan* plan)
 {

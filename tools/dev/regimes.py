@@ -68,7 +68,7 @@ def case(name, W, src_rows, oy, orows, F, with_map, knobs, queued_n=50):
         q = queued_us(fn, queued_n)
         px = W * orows * F
         print("%-28s pairs/SM %d minRows %3d : one call median %8.1f us (min %8.1f)  queued %8.1f us/call = %9.0f Mpix/s  ssim %.6f" %
-              (name, pairs or 8, min_rows or 12, med, mn, q, px / q, float(val[0].item())), flush=True)
+              (name, pairs or 8, min_rows or 6, med, mn, q, px / q, float(val[0].item())), flush=True)
     lib.ssim_cuda_set_tuning(0, 0)
 
 
