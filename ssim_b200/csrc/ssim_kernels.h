@@ -94,8 +94,12 @@ constexpr uint32_t kCrossingUnits = 9;   // what it costs a team to start a seco
 inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint32_t frames, uint32_t minUnits, SlotPlan* plan)
 {
     const unsigned long long bands = ((unsigned long long)width + kBandW - 1) / kBandW;
-    const unsigned long long colUnits = (unsigned long long)outRows + kPad;
-    if (maxSlots < 1 || width == 0 || outRows == 0 || frames == 0 || bands * frames > 0x7fffffffull || bands * frames * colUnits > 0x7fffffffull) return false;
+    // the padding units in front of a column stand for what a team pays when its range crosses into that column: the 10
+    // start-up rows of the new piece plus the refill of its pipeline (kCrossingUnits) -- with that in the line, teams whose
+    // ranges cross a boundary get fewer rows and finish with the others
+    // (a single column has no crossings)
+    const unsigned long long maxColUnits = (unsigned long long)outRows + kPad + kCrossingUnits;
+    if (maxSlots < 1 || width == 0 || outRows == 0 || frames == 0 || bands * frames > 0x7fffffffull || bands * frames * maxColUnits > 0x7fffffffull) return false;
     if (minUnits < 1) minUnits = 1;
     // team size: as many adjacent bands as possible side by side, as long as ragged last groups and slots that do not
     // fill a team waste less than the sharing is worth (an unshared band edge costs about a tenth of a band's time)
@@ -110,23 +114,26 @@ inline bool plan_slots(uint32_t maxSlots, uint32_t width, uint32_t outRows, uint
     }
     const unsigned long long group = bestG, groupsPerFrame = (bands + group - 1) / group;
     const unsigned long long cols = groupsPerFrame * frames;
+    const unsigned long long pad = cols > 1 ? kPad + kCrossingUnits : kPad;
+    const unsigned long long colUnits = (unsigned long long)outRows + pad;
     unsigned long long units = cols * colUnits;                                    // per team member
     const unsigned long long maxTeams = maxSlots / group;
     unsigned long long teams = units / minUnits;
     if (teams > maxTeams) teams = maxTeams;
     if (teams < 1) teams = 1;
     plan->group = (uint32_t)group;
-    plan->pad = kPad;
+    plan->pad = (uint32_t)pad;
     plan->colUnits = (uint32_t)colUnits;
     // Few columns, many teams (a single image): cutting every column into k equal parts -- the column is padded up to
     // k * Q units -- leaves some teams idle but spares all others the second piece that a range crossing a column boundary
     // means.  Taken when it is the faster of the two by the model "time = units + start-up rows (+ a crossing)".
     if (cols > 1 && cols <= maxTeams) {
+        const unsigned long long partUnits = (unsigned long long)outRows + kPad;   // no crossings: plain start-up rows
         unsigned long long k = maxTeams / cols;
-        while (k > 1 && (colUnits + k - 1) / k < minUnits) --k;
-        const unsigned long long partQ = (colUnits + k - 1) / k;
+        while (k > 1 && (partUnits + k - 1) / k < minUnits) --k;
+        const unsigned long long partQ = (partUnits + k - 1) / k;
         const unsigned long long lineQ = (units + teams - 1) / teams;
-        if (partQ >= minUnits && partQ < lineQ + kCrossingUnits && k * partQ * cols <= 0x7fffffffull) {
+        if (partQ >= minUnits && partQ <= lineQ && k * partQ * cols <= 0x7fffffffull) {
             teams = k * cols;
             plan->colUnits = (uint32_t)(k * partQ);
             plan->pad = (uint32_t)(k * partQ - outRows);

@@ -27,7 +27,9 @@ static void check(uint32_t maxSlots, uint32_t w, uint32_t h, uint32_t f, uint32_
     expect((uint64_t)teams * plan.shareQ + plan.shareR == (uint64_t)g.groupsPerFrame * f * plan.colUnits, "shares add up to all units", w, h, f, plan.slots);
     expect(plan.shareQ >= (teams > 1 ? minUnits : 1u), "no team thinner than minUnits", w, h, f, plan.slots);
     expect(plan.pad >= 10 && plan.colUnits == h + plan.pad, "columns are the rows plus at least 10 padding units", w, h, f, plan.slots);
-    expect(plan.pad == 10 || (plan.shareR == 0 && plan.colUnits % plan.shareQ == 0), "padded columns are cut into equal parts", w, h, f, plan.slots);
+    const bool oneColumn = (uint64_t)g.groupsPerFrame * f == 1;
+    expect(plan.pad == (oneColumn ? 10u : 19u) || (plan.shareR == 0 && plan.colUnits % plan.shareQ == 0),
+           "padding is the start-up rows (+ the crossing cost when there are several columns), or the columns are cut into equal parts", w, h, f, plan.slots);
     expect((uint64_t)g.groupsPerFrame * plan.group >= bands && (uint64_t)(g.groupsPerFrame - 1) * plan.group < bands, "groups cover the bands", w, h, f, plan.slots);
     expect((double)bands / ((double)g.groupsPerFrame * plan.group) >= 0.9 || bands < 8, "little ragged waste", w, h, f, plan.slots);
     {
@@ -84,9 +86,9 @@ int main()
     check(1, 3840, 2160, 2, 24);
     // the documented plans
     ssimk::SlotPlan p;
-    ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p);   expect(p.group == 6 && p.slots == 1140 && p.shareQ == 115 && p.shareR == 0 && p.pad == 25, "one 4K pair: 10 columns of 6 bands cut into 19 equal parts of 115 units", 3840, 2160, 1, p.slots);
-    ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p);  expect(p.group == 6 && p.slots == 1182 && p.shareQ == 7049, "64 x 4K", 3840, 2160, 64, p.slots);
-    ssimk::plan_slots(slots, 16384, 2058, 1, 24, &p);  expect(p.group == 8 && p.slots == 1184 && p.pad == 10, "a 16384-wide strip: one team of 8 bands per CTA, ranges cross columns", 16384, 2058, 1, p.slots);
+    ssimk::plan_slots(slots, 3840, 2160, 1, 24, &p);   expect(p.group == 6 && p.slots == 1182 && p.shareQ == 110 && p.pad == 19, "one 4K pair: 197 teams of 6 bands share 10 columns of 2160 + 19 units", 3840, 2160, 1, p.slots);
+    ssimk::plan_slots(slots, 3840, 2160, 64, 24, &p);  expect(p.group == 6 && p.slots == 1182 && p.shareQ == 7078, "64 x 4K", 3840, 2160, 64, p.slots);
+    ssimk::plan_slots(slots, 16384, 2058, 1, 24, &p);  expect(p.group == 8 && p.slots == 1184 && p.pad == 19, "a 16384-wide strip: one team of 8 bands per CTA, ranges cross columns", 16384, 2058, 1, p.slots);
     ssimk::plan_slots(slots, 1920, 1080, 1, 24, &p);   expect(p.group == 6 && p.slots == 1170 && p.shareQ == 28 && p.pad == 12, "1080p: 5 columns of 6 bands cut into 39 equal parts of 28 units", 1920, 1080, 1, p.slots);
     ssimk::plan_slots(slots, 333, 141, 1, 24, &p);     expect(p.group == 6 && p.slots == 36, "small image: fewer slots", 333, 141, 1, p.slots);
     ssimk::plan_slots(slots, 8, 8, 1, 24, &p);         expect(p.slots == 1 && p.shareQ == 18, "tiny image: one slot", 8, 8, 1, p.slots);

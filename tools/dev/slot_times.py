@@ -39,7 +39,10 @@ def run(W, H, F, with_map=True):
     order = np.argsort(-end)[:12]
     print("   slowest slots (slot: start, finish us):", " ".join("%d: %.1f-%.1f" % (i, start[i], end[i]) for i in order))
 
-run(3840, 2160, 1)
-run(3840, 2160, 16)
-run(3840, 2160, 64)
-run(1920, 1080, 1, False)
+if len(sys.argv) > 3:
+    run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), len(sys.argv) <= 4)
+else:
+    run(3840, 2160, 1)
+    run(3840, 2160, 16)
+    run(3840, 2160, 64)
+    run(1920, 1080, 1, False)
