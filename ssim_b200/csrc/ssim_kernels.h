@@ -65,8 +65,9 @@ template <bool kU16> struct PixGeo {
 // rows at unrelated times each fetch them from DRAM again.  Measured with every pair on its own: 4.0x the algorithmic DRAM
 // read traffic, 1.05 GB instead of 265 MB for 16 4K pairs, and 10% less throughput.)
 // The work is laid out as one line per team member: a COLUMN is one group of bands of one frame (cols = frames x
-// groupsPerFrame, frame-major), every column is `outRows` rows long and is preceded by kPad = 2*kHalo "padding" units that
-// stand for the cost of starting a piece (the 10 extra input rows the vertical filter needs before its first output).
+// groupsPerFrame, frame-major), every column is `outRows` rows long and is preceded by `pad` "padding" units that stand
+// for the cost of crossing into it: kPad = 2*kHalo start-up rows (the 10 extra input rows the vertical filter needs before
+// its first output) + kCrossingUnits for the refill of the pair's pipeline.
 // Team j owns the units [j*Q + min(j,R), ...) of that line (Q, R = quotient and remainder of units / teams), i.e. every team
 // owns the same number of units +-1; the rows of a column that fall into a team's range form a PIECE per member, which is
 // what a warp pair processes in one go (own halo above and below, replicated rows at the plane's edges).  A range that
@@ -83,7 +84,7 @@ struct SlotPlan {
     uint32_t group;          // pairs per team = adjacent bands walked side by side
     uint32_t shareQ, shareR; // units per team: team j owns shareQ + (j < shareR) units
     uint32_t colUnits;       // units per column = outRows + pad
-    uint32_t pad;            // padding units in front of every column: kPad, or more when the columns are cut into equal parts
+    uint32_t pad;            // padding units in front of every column: kPad (one column), kPad + kCrossingUnits, or more when the columns are cut into equal parts
 };
 constexpr uint32_t kCrossingUnits = 9;   // what it costs a team to start a second piece (its range crosses into the next column),
                                          // in row units: measured, the crossing teams of a 4K pair finish 3 us after the others
