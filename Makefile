@@ -1,6 +1,7 @@
 # Builds the product libraries in-tree:
 #   ssim_b200/lib/libssim_cuda.so   C-ABI shim + sm_100a kernels   (include/ssim_cuda.h)
 #   ssim_b200/lib/librmgr-ssim.so   the reference's C/C++ API      (include/rmgr/ssim.h, ssim-openmp.h)
+#   ssim_b200/lib/libssim_imgio.so  the front end's JPEG reader    (include/ssim_imgio.h; host code)
 # `make oracle` builds the CPU checkers (test infrastructure) under oracle/.
 NVCC    ?= /usr/local/cuda/bin/nvcc
 HOSTCXX ?= /usr/bin/g++
@@ -12,7 +13,7 @@ OBJ     := build/obj
 
 BIN     := ssim_b200/bin
 
-all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so $(BIN)/rmgr-ssim $(BIN)/latency_client
+all: $(LIB)/libssim_cuda.so $(LIB)/librmgr-ssim.so $(LIB)/libssim_imgio.so $(BIN)/rmgr-ssim $(BIN)/latency_client
 
 $(OBJ)/%.o: $(CSRC)/%.cu $(CSRC)/ssim_kernels.h $(CSRC)/synth.h include/ssim_cuda.h
 	@mkdir -p $(OBJ)
@@ -29,8 +30,12 @@ $(LIB)/libssim_cuda.so: $(OBJ)/ssim_kernels.o $(OBJ)/ssim_cuda.o
 $(LIB)/librmgr-ssim.so: $(OBJ)/rmgr_api.o $(LIB)/libssim_cuda.so
 	$(HOSTCXX) -shared -o $@ $(OBJ)/rmgr_api.o -L$(LIB) -lssim_cuda -Wl,-rpath,'$$ORIGIN'
 
+$(LIB)/libssim_imgio.so: $(CSRC)/imgio.cpp $(CSRC)/jpeg_reader.h include/ssim_imgio.h
+	@mkdir -p $(LIB)
+	$(HOSTCXX) -O2 -std=c++17 -fPIC -shared -DNDEBUG -Wall -Wextra -Iinclude -o $@ $(CSRC)/imgio.cpp
+
 # rmgr-ssim: the reference's CLI (src/ssim-cli.cpp) re-done on top of the public API; PNG/PNM I/O via zlib
-$(BIN)/rmgr-ssim: $(CSRC)/ssim_cli.cpp $(LIB)/librmgr-ssim.so $(LIB)/libssim_cuda.so
+$(BIN)/rmgr-ssim: $(CSRC)/ssim_cli.cpp $(CSRC)/jpeg_reader.h $(LIB)/librmgr-ssim.so $(LIB)/libssim_cuda.so
 	@mkdir -p $(BIN)
 	$(HOSTCXX) -O2 -std=c++17 -Iinclude -o $@ $(CSRC)/ssim_cli.cpp -L$(LIB) -lrmgr-ssim -lssim_cuda -lz -Wl,-rpath,'$$ORIGIN/../lib'
 

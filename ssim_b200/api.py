@@ -2,6 +2,7 @@
 
   librmgr-ssim.so   the reference's C API  -- rmgr_ssim_compute_ssim() & friends (include/rmgr/ssim.h)
   libssim_cuda.so   the C-ABI CUDA engine  -- ssim_cuda_*()                      (include/ssim_cuda.h)
+  libssim_imgio.so  the front end's JPEG reader -- ssim_imgio_decode_jpeg()      (include/ssim_imgio.h; host code)
 
 There is no CPU fallback: importing works anywhere, but every compute call needs the built libraries and a
 B200; a missing library raises immediately (RuntimeError) instead of degrading."""
@@ -210,3 +211,30 @@ def compute_channels(a, b, want_map=False, device=0):
 
 def synth_fill(device, stream, d_a, pitch_a, d_b, pitch_b, width, rows, y0=0, frame=0, seed=0x5517):
     _check(cuda_lib().ssim_cuda_synth_fill(device, stream, d_a, pitch_a, d_b, pitch_b, width, rows, y0, frame, seed))
+
+
+def imgio_lib():
+    """libssim_imgio.so with argtypes declared for every symbol of include/ssim_imgio.h."""
+    lib = _load("libssim_imgio.so")
+    if not getattr(lib, "_bound", False):
+        lib.ssim_imgio_decode_jpeg.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.ssim_imgio_decode_jpeg.restype = C.c_int
+        lib.ssim_imgio_last_error.restype = C.c_char_p
+        lib._bound = True
+    return lib
+
+
+def decode_jpeg(data):
+    """JPEG bytes (bytes or a uint8 array) -> uint8 array (h, w) or (h, w, 3), decoded like the reference's image loader
+    (stbi_load, src/ssim-cli.cpp:143).  Raises ValueError on a corrupt or unsupported file."""
+    lib = imgio_lib()
+    buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.ssim_imgio_decode_jpeg(buf.ctypes.data, buf.size, None, 0, C.byref(w), C.byref(h), C.byref(c))
+    if rc:
+        raise ValueError("JPEG: " + lib.ssim_imgio_last_error().decode())
+    out = np.empty((h.value, w.value, c.value), dtype=np.uint8)
+    rc = lib.ssim_imgio_decode_jpeg(buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(c))
+    if rc:
+        raise ValueError("JPEG: " + lib.ssim_imgio_last_error().decode())
+    return out[:, :, 0].copy() if c.value == 1 else out

@@ -9,8 +9,9 @@
 // .png / .bmp / .tga / .pgm / .ppm.
 //
 // The reference decodes images with stb_image, which it downloads at configure time and which is not available
-// offline; this front end carries its own small readers instead: binary PNM (P5/P6, maxval 255) and PNG (8-bit
-// gray, gray+alpha, RGB, RGBA, palette; non-interlaced) on top of zlib.  JPEG is not supported.
+// offline; this front end carries its own small readers instead: binary PNM (P5/P6, maxval 255), PNG (8-bit
+// gray, gray+alpha, RGB, RGBA, palette; non-interlaced) on top of zlib, and JPEG (baseline / progressive, jpeg_reader.h:
+// pixel-identical to the decoder the reference uses, so its JPEG-based known answers hold here).
 // All SSIM work goes through the public API of this repository (include/rmgr/ssim.h, include/ssim_cuda.h);
 // the -y luma conversion runs on the GPU (ssim_cuda_compute_luma).
 #include <rmgr/ssim.h>
@@ -25,6 +26,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include "jpeg_reader.h"
 
 namespace
 {
@@ -170,7 +173,13 @@ bool load_img(const char* path, Image& img)
     bool ok;
     if (d.size() > 8 && !memcmp(d.data(), pngSig, 8)) ok = decode_png(d, img);
     else if (d.size() > 2 && d[0] == 'P' && (d[1] == '5' || d[1] == '6')) ok = decode_pnm(d, img);
-    else { g_error = "unknown image format (supported: PNG, binary PGM/PPM)"; ok = false; }
+    else if (d.size() > 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) {
+        jpegr::Decoder dec;
+        ok = dec.decode(d.data(), d.size());
+        if (ok) { img.width = dec.width; img.height = dec.height; img.channels = dec.channels; img.pixels.swap(dec.pixels); }
+        else g_error = dec.error;
+    }
+    else { g_error = "unknown image format (supported: PNG, JPEG, binary PGM/PPM)"; ok = false; }
     if (!ok) fprintf(stderr, "Failed to load image \"%s\":\n%s\n", path, g_error.c_str());
     return ok;
 }
@@ -257,7 +266,7 @@ void print_help(FILE* file)
                   "  -y  Compute SSIM on luminance\n"
                   "      For images with <= 2 channels, only channel 0's SSIM will be computed\n"
                   "      For images with >= 3 channels, first three channels are converted from RGB to Y\n\n"
-                  "Images: PNG (8-bit, non-interlaced) or binary PGM/PPM.  Map: .pfm, .png, .bmp, .tga, .pgm/.ppm\n"
+                  "Images: PNG (8-bit, non-interlaced), JPEG or binary PGM/PPM.  Map: .pfm, .png, .bmp, .tga, .pgm/.ppm\n"
                   "Backend: ssim_b200 (CUDA sm_100a), device selected by SSIM_CUDA_DEVICE\n");
 }
 

@@ -53,7 +53,7 @@ def einstein():
 
 @pytest.fixture(scope="session")
 def bbb360_full():
-    """big_buck_bunny_360_07806 PNG and JPEG q50 (libjpeg-decoded), full 640x360 RGB frames"""
+    """big_buck_bunny_360_07806 PNG and JPEG q50 (decoded by ssim_b200/csrc/jpeg_reader.h: the pixels the reference's loader makes), full 640x360 RGB frames"""
     return dict(np.load(os.path.join(GOLDEN_DIR, "bbb360.npz")))
 
 

@@ -3,10 +3,14 @@
 
     python tests/golden/make_golden.py
 
-Inputs : /root/reference/tests/images (PNG decoded with PIL; JPEG decoded with PIL/libjpeg -- NOT stb_image,
-         so the bbb* fixtures are live-parity inputs, not the reference's hard-coded bbb goldens).
-Outputs: decoded pixels + what the UNMODIFIED reference build (oracle/_ref) returns for them.
+Inputs : /root/reference/tests/images.  PNG decoded with PIL (lossless: decoder-independent); JPEG decoded with this
+         repository's own reader (ssim_b200/csrc/jpeg_reader.h through libssim_imgio.so), whose pixels are identical to
+         those of the decoder the reference's tests use -- checked below: the reference's hard-coded bbb known answers
+         (tests/rmgr-ssim-tests.cpp:388-465, 132 numbers) are reproduced to 1e-13 by its own naive template on them.
+Outputs: decoded pixels, the 360p JPEG files themselves (as bytes: the GPU box decodes them with the same reader), what the
+         UNMODIFIED reference build (oracle/_ref) returns for them, and the reference's known answers.
 The six einstein known answers are the reference's own constants (tests/rmgr-ssim-tests.cpp:354-359)."""
+import re
 import json
 import os
 import sys
@@ -17,6 +21,7 @@ from PIL import Image
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
+import ssim_b200.api as api  # noqa: E402
 from ssim_b200.synth import checksum, synth_pair  # noqa: E402
 
 IMAGES = "/root/reference/tests/images"
@@ -36,8 +41,49 @@ EDGE_DIMS = [(1, 1), (2, 3), (7, 3), (5, 5), (11, 11), (16, 16), (255, 63), (256
              (1, 300), (513, 129), (64, 75), (65, 11), (130, 200)]
 
 
+QUALITIES = list(range(0, 101, 10))
+
+
 def f32(x):
     return float(np.float32(x))
+
+
+def load_jpeg(stub, quality):
+    with open(os.path.join(IMAGES, "%s_%02d.jpg" % (stub, quality)), "rb") as fh:
+        data = fh.read()
+    return data, api.decode_jpeg(data)
+
+
+def reference_bbb_constants():
+    """The 4 x 11 x 3 known answers of the reference's bbb suites, as the strings its test file holds
+    (tests/rmgr-ssim-tests.cpp:388-465): suite -> [quality 0, 10, .. 100][channel]."""
+    text = open("/root/reference/tests/rmgr-ssim-tests.cpp").read()
+    out = {}
+    for suite in ("bbb360", "bbb1080", "bbb255", "bbb257"):
+        body = text[text.index("static void test_%s(" % suite):]
+        body = body[:body.index("test_bbb(")]
+        rows = re.findall(r"REF_SSIM3\(\s*([0-9.]+)\s*,\s*([0-9.]+)\s*,\s*([0-9.]+)\s*\)", body)
+        assert len(rows) == 11, (suite, len(rows))
+        out[suite] = [list(r) for r in rows]
+    return out
+
+
+def pin_decoder(consts):
+    """Every one of the reference's 132 bbb known answers from ITS files, OUR reader and ITS naive template: |d| <= 1e-13
+    (REF_TOLERANCE, tests/rmgr-ssim-tests.cpp:72).  A single differing pixel moves these means by ~1e-8."""
+    worst = 0.0
+    for suite, stub, (w, h) in (("bbb360", "big_buck_bunny_360_07806", (640, 360)), ("bbb1080", "big_buck_bunny_1080_07806", (1920, 1080)),
+                                ("bbb255", "big_buck_bunny_360_07806", (255, 63)), ("bbb257", "big_buck_bunny_360_07806", (257, 65))):
+        png = np.asarray(Image.open(os.path.join(IMAGES, stub + ".png")).convert("RGB"), dtype=np.uint8)
+        for qi, q in enumerate(QUALITIES):
+            _, jpg = load_jpeg(stub, q)
+            for ch in range(3):
+                mean, _ = oracle.naive_ssim(np.ascontiguousarray(png[:h, :w, ch]), np.ascontiguousarray(jpg[:h, :w, ch]))
+                d = abs(mean - float(consts[suite][qi][ch]))
+                worst = max(worst, d)
+                assert d <= 1e-13, (suite, q, ch, mean, consts[suite][qi][ch])
+    print("JPEG reader pinned: 132 reference known answers reproduced, worst |d| = %.1e" % worst)
+    return worst
 
 
 def main():
@@ -67,12 +113,17 @@ def main():
 
     # ---- bbb 360p: RGB interleaved (step=3), crops 255x63 / 257x65 with the full-frame stride kept
     png = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_360_07806.png")).convert("RGB"), dtype=np.uint8)
-    jpg = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_360_07806_50.jpg")).convert("RGB"), dtype=np.uint8)
+    _, jpg = load_jpeg("big_buck_bunny_360_07806", 50)
     assert png.shape == (360, 640, 3) and jpg.shape == png.shape
     np.savez_compressed(os.path.join(OUT, "bbb360.npz"), png=png, jpg50=jpg)       # the full frames; tests slice the top 80 rows
+    # the eleven 360p JPEG files as bytes (0.7 MB): decoded on the spot by the tests with the same reader
+    np.savez(os.path.join(OUT, "bbb360_jpeg_files.npz"),
+             **{"q%02d" % q: np.frombuffer(load_jpeg("big_buck_bunny_360_07806", q)[0], dtype=np.uint8) for q in QUALITIES})
+    consts = reference_bbb_constants()
+    worst = pin_decoder(consts)
     bbb = {}
     # full frames, all three channels, and the 1080p frame (green channel only: fixture size), like the reference's
-    # tests/rmgr-ssim-tests.cpp:388-425 (whose hard-coded constants were made with stb_image's JPEG decoder, not libjpeg)
+    # tests/rmgr-ssim-tests.cpp:388-425
     for ch in range(3):
         kw = dict(step_a=3, step_b=3, stride_a=640 * 3, stride_b=640 * 3, width=640, height=360, a_off=ch, b_off=ch)
         r64a, m64a = oracle.ref_ssim("f64", jpg, png, want_map=True, **kw)
@@ -80,7 +131,7 @@ def main():
         bbb["640x360_ch%d" % ch] = {"ref_f64_auto": f32(r64a), "ref_f32_auto_openmp": f32(r32), "ref_f64_auto_map_sum64": float(m64a.astype(np.float64).sum()),
                                     "ref_f64_auto_map_min": f32(m64a.min())}
     big_png = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_1080_07806.png")).convert("RGB"), dtype=np.uint8)[..., 1].copy()
-    big_jpg = np.asarray(Image.open(os.path.join(IMAGES, "big_buck_bunny_1080_07806_50.jpg")).convert("RGB"), dtype=np.uint8)[..., 1].copy()
+    big_jpg = load_jpeg("big_buck_bunny_1080_07806", 50)[1][..., 1].copy()
     assert big_png.shape == (1080, 1920)
     np.savez_compressed(os.path.join(OUT, "bbb1080_green.npz"), png=big_png, jpg50=big_jpg)
     r64a, m64a = oracle.ref_ssim("f64", big_jpg, big_png, want_map=True)
@@ -142,6 +193,9 @@ def main():
 
     with open(os.path.join(OUT, "golden.json"), "w") as fh:
         json.dump({"einstein": ein, "bbb360_jpg50": bbb, "synthetic": syn, "u16_naive": u16,
+                   "bbb_reference": {"known_answers": consts, "qualities": QUALITIES, "decoder_pin_worst_abs_diff": worst,
+                                     "source": "tests/rmgr-ssim-tests.cpp:388-465 of the reference (double means of its naive template); "
+                                               "suite -> [quality][channel]; bbb255 / bbb257 are the 255x63 / 257x65 crops of the 360p frame"},
                    "note": "ref_* values are float32 results of the unmodified reference build (oracle/_ref), repr as double"},
                   fh, indent=1, sort_keys=True)
     print("wrote", OUT)
