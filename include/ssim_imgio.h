@@ -19,7 +19,8 @@ extern "C" {
  *   out == NULL : only *width, *height, *channels are filled (the file is parsed completely);
  *   out != NULL : must hold width*height*channels bytes (capacity given in out_capacity); receives the pixels interleaved
  *                 (gray, or RGB), rows top-down, no padding.
- * Returns 0, EINVAL (not a JPEG / corrupt / unsupported variant: see ssim_imgio_last_error()) or ERANGE (out too small). */
+ * Returns 0, EINVAL (not a JPEG / corrupt / unsupported variant / more than 2^28 pixels: see ssim_imgio_last_error()),
+ * ERANGE (out too small) or ENOMEM. */
 int ssim_imgio_decode_jpeg(const uint8_t* data, size_t size, uint8_t* out, size_t out_capacity,
                            int* width, int* height, int* channels);
 

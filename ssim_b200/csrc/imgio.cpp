@@ -3,6 +3,7 @@
 #include <ssim_imgio.h>
 
 #include <cerrno>
+#include <new>
 
 #include "jpeg_reader.h"
 
@@ -13,14 +14,16 @@ extern "C" int ssim_imgio_decode_jpeg(const uint8_t* data, size_t size, uint8_t*
 {
     t_error.clear();
     if (!data || !width || !height || !channels) { t_error = "null argument"; return EINVAL; }
-    jpegr::Decoder dec;
-    if (!dec.decode(data, size)) { t_error = dec.error; return EINVAL; }
-    *width = dec.width; *height = dec.height; *channels = dec.channels;
-    if (out) {
-        if (out_capacity < dec.pixels.size()) { t_error = "output buffer too small"; return ERANGE; }
-        memcpy(out, dec.pixels.data(), dec.pixels.size());
-    }
-    return 0;
+    try {
+        jpegr::Decoder dec;
+        if (!dec.decode(data, size)) { t_error = dec.error; return EINVAL; }
+        *width = dec.width; *height = dec.height; *channels = dec.channels;
+        if (out) {
+            if (out_capacity < dec.pixels.size()) { t_error = "output buffer too small"; return ERANGE; }
+            memcpy(out, dec.pixels.data(), dec.pixels.size());
+        }
+        return 0;
+    } catch (const std::bad_alloc&) { t_error = "out of memory"; return ENOMEM; }
 }
 
 extern "C" const char* ssim_imgio_last_error(void) { return t_error.c_str(); }

@@ -90,6 +90,7 @@ public:
     {
         d_ = data; n_ = size; pos_ = 0;
         progressive_ = false; restartInterval_ = 0; haveFrame_ = false; jfif_ = false; adobeTransform_ = -1;
+        pendingMarker_ = -1; memset(quant_, 0, sizeof(quant_)); memset(haveQuant_, 0, sizeof(haveQuant_));
         if (n_ < 4 || d_[0] != 0xFF || d_[1] != 0xD8) return fail("not a JPEG");
         pos_ = 2;
         for (;;) {
@@ -103,6 +104,7 @@ public:
             if (!read_segment(m)) return false;
         }
         if (!haveFrame_) return fail("no frame header");
+        for (size_t k = 0; k < comps_.size(); ++k) if (!haveQuant_[comps_[k].tq]) return fail("missing quantisation table");
         if (progressive_) finish_progressive();
         return convert();
     }
@@ -114,6 +116,7 @@ private:
     int adobeTransform_;
     int restartInterval_;
     uint16_t quant_[4][64];      // natural order
+    bool haveQuant_[4];
     Huffman dc_[4], ac_[4];
     std::vector<Component> comps_;
     int hMax_, vMax_, mcuX_, mcuY_;
@@ -151,6 +154,7 @@ private:
                     const int pq = u8(), prec = pq >> 4, t = pq & 15;
                     if (prec > 1 || t > 3) return fail("bad DQT");
                     for (int i = 0; i < 64; ++i) quant_[t][kZigzag[i]] = (uint16_t)(prec ? u16() : u8());
+                    haveQuant_[t] = true;
                 }
                 break;
             case 0xC4:                                              // DHT
@@ -191,6 +195,7 @@ private:
         height = u16(); width = u16();
         const int nc = u8();
         if (width <= 0 || height <= 0) return fail("bad JPEG dimensions");
+        if ((uint64_t)width * (uint64_t)height > (1ull << 28)) return fail("JPEG larger than 2^28 pixels");
         if (nc != 1 && nc != 3) return fail("unsupported JPEG component count (1 or 3 expected)");
         if (end - pos_ < (size_t)(3 * nc)) return fail("bad SOF");
         comps_.assign((size_t)nc, Component());
@@ -310,14 +315,14 @@ private:
         const Huffman &hd = dc_[c.td], &ha = ac_[c.ta];
         const int t = decode_symbol(hd);
         if (t < 0 || t > 15) return fail("bad Huffman code");
-        c.dcPred += extend_receive(t);
-        blk[0] = (short)(c.dcPred * quant_[c.tq][0]);
+        c.dcPred = (int)((uint32_t)c.dcPred + (uint32_t)extend_receive(t));
+        blk[0] = (short)((uint32_t)c.dcPred * quant_[c.tq][0]);
         for (int k = 1; k < 64;) {
             const int rs = decode_symbol(ha);
             if (rs < 0) return fail("bad Huffman code");
             const int s = rs & 15, r = rs >> 4;
             if (s == 0) { if (rs != 0xF0) break; k += 16; }
-            else { k += r; const int z = kZigzag[k++]; blk[z] = (short)(extend_receive(s) * quant_[c.tq][z]); }
+            else { k += r; const int z = kZigzag[k++]; blk[z] = (short)((uint32_t)extend_receive(s) * quant_[c.tq][z]); }
         }
         return true;
     }
@@ -327,8 +332,8 @@ private:
             memset(blk, 0, 64 * sizeof(short));
             const int t = decode_symbol(dc_[c.td]);
             if (t < 0 || t > 15) return fail("bad Huffman code");
-            c.dcPred += extend_receive(t);
-            blk[0] = (short)(c.dcPred * (1 << al_));
+            c.dcPred = (int)((uint32_t)c.dcPred + (uint32_t)extend_receive(t));
+            blk[0] = (short)((uint32_t)c.dcPred << al_);
         } else if (get_bit()) blk[0] = (short)(blk[0] + (1 << al_));
         return true;
     }
@@ -448,7 +453,7 @@ private:
             for (int by = 0; by < bh; ++by)
                 for (int bx = 0; bx < bw; ++bx) {
                     short* b = &c.coeff[64 * ((size_t)by * c.coeffW + bx)];
-                    for (int i = 0; i < 64; ++i) b[i] = (short)(b[i] * quant_[c.tq][i]);
+                    for (int i = 0; i < 64; ++i) b[i] = (short)((uint32_t)(int)b[i] * quant_[c.tq][i]);
                     idct(&c.plane[(size_t)by * 8 * c.w2 + (size_t)bx * 8], c.w2, b);
                 }
         }
@@ -457,28 +462,40 @@ private:
     // ---- inverse DCT: 12-bit fixed-point Loeffler/IJG "islow" butterflies; the column pass keeps 2 extra bits
     static inline int fx(float x) { return (int)(x * 4096 + 0.5); }     // float constant, sum in double, truncation (also for negatives)
     static inline uint8_t clamp8(int x) { return (unsigned)x > 255 ? (x < 0 ? 0 : 255) : (uint8_t)x; }
-    struct Idct1D { int x0, x1, x2, x3, t0, t1, t2, t3; };
-    static inline void idct_1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7, Idct1D& o)
+    // 32-bit two's-complement arithmetic that wraps instead of overflowing: valid streams never get near the limit, corrupt ones
+    // (coefficients of +-32767 under 16-bit quantisers) do, and a file must not be able to trigger undefined behaviour
+    struct W {
+        uint32_t v;
+        W() : v(0) {}
+        W(int x) : v((uint32_t)x) {}
+        static W raw(uint32_t u) { W w; w.v = u; return w; }
+        friend W operator+(W a, W b) { return raw(a.v + b.v); }
+        friend W operator-(W a, W b) { return raw(a.v - b.v); }
+        friend W operator*(W a, W b) { return raw(a.v * b.v); }
+        int shr(int n) const { return (int)(int32_t)v >> n; }           // arithmetic shift of the signed value
+    };
+    struct Idct1D { W x0, x1, x2, x3, t0, t1, t2, t3; };
+    static inline void idct_1d(W s0, W s1, W s2, W s3, W s4, W s5, W s6, W s7, Idct1D& o)
     {
         static const int c0541 = fx(0.5411961f), c1847 = fx(-1.847759065f), c0765 = fx(0.765366865f), c1175 = fx(1.175875602f),
                          c0298 = fx(0.298631336f), c2053 = fx(2.053119869f), c3072 = fx(3.072711026f), c1501 = fx(1.501321110f),
                          c0899 = fx(-0.899976223f), c2562 = fx(-2.562915447f), c1961 = fx(-1.961570560f), c0390 = fx(-0.390180644f);
-        int p1 = (s2 + s6) * c0541;
-        int t2 = p1 + s6 * c1847;
-        int t3 = p1 + s2 * c0765;
-        int t0 = (s0 + s4) * 4096;
-        int t1 = (s0 - s4) * 4096;
+        W p1 = (s2 + s6) * W(c0541);
+        W t2 = p1 + s6 * W(c1847);
+        W t3 = p1 + s2 * W(c0765);
+        W t0 = (s0 + s4) * W(4096);
+        W t1 = (s0 - s4) * W(4096);
         o.x0 = t0 + t3; o.x3 = t0 - t3; o.x1 = t1 + t2; o.x2 = t1 - t2;
         t0 = s7; t1 = s5; t2 = s3; t3 = s1;
-        int p3 = t0 + t2, p4 = t1 + t3;
+        W p3 = t0 + t2, p4 = t1 + t3;
         p1 = t0 + t3;
-        int p2 = t1 + t2;
-        const int p5 = (p3 + p4) * c1175;
-        t0 *= c0298; t1 *= c2053; t2 *= c3072; t3 *= c1501;
-        p1 = p5 + p1 * c0899;
-        p2 = p5 + p2 * c2562;
-        p3 *= c1961;
-        p4 *= c0390;
+        W p2 = t1 + t2;
+        const W p5 = (p3 + p4) * W(c1175);
+        t0 = t0 * W(c0298); t1 = t1 * W(c2053); t2 = t2 * W(c3072); t3 = t3 * W(c1501);
+        p1 = p5 + p1 * W(c0899);
+        p2 = p5 + p2 * W(c2562);
+        p3 = p3 * W(c1961);
+        p4 = p4 * W(c0390);
         o.t3 = t3 + p1 + p4; o.t2 = t2 + p2 + p3; o.t1 = t1 + p2 + p4; o.t0 = t0 + p1 + p3;
     }
     static void idct(uint8_t* out, int stride, const short* d)
@@ -487,21 +504,22 @@ private:
         Idct1D r;
         for (int i = 0; i < 8; ++i) {                               // columns
             idct_1d(d[i], d[8 + i], d[16 + i], d[24 + i], d[32 + i], d[40 + i], d[48 + i], d[56 + i], r);
-            r.x0 += 512; r.x1 += 512; r.x2 += 512; r.x3 += 512;
-            val[i]      = (r.x0 + r.t3) >> 10; val[56 + i] = (r.x0 - r.t3) >> 10;
-            val[8 + i]  = (r.x1 + r.t2) >> 10; val[48 + i] = (r.x1 - r.t2) >> 10;
-            val[16 + i] = (r.x2 + r.t1) >> 10; val[40 + i] = (r.x2 - r.t1) >> 10;
-            val[24 + i] = (r.x3 + r.t0) >> 10; val[32 + i] = (r.x3 - r.t0) >> 10;
+            const W h(512);
+            r.x0 = r.x0 + h; r.x1 = r.x1 + h; r.x2 = r.x2 + h; r.x3 = r.x3 + h;
+            val[i]      = (r.x0 + r.t3).shr(10); val[56 + i] = (r.x0 - r.t3).shr(10);
+            val[8 + i]  = (r.x1 + r.t2).shr(10); val[48 + i] = (r.x1 - r.t2).shr(10);
+            val[16 + i] = (r.x2 + r.t1).shr(10); val[40 + i] = (r.x2 - r.t1).shr(10);
+            val[24 + i] = (r.x3 + r.t0).shr(10); val[32 + i] = (r.x3 - r.t0).shr(10);
         }
         for (int i = 0; i < 8; ++i, out += stride) {                // rows; 1 << 17 to remove, + 128 level shift
             const int* v = val + 8 * i;
             idct_1d(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], r);
-            const int bias = 65536 + (128 << 17);
-            r.x0 += bias; r.x1 += bias; r.x2 += bias; r.x3 += bias;
-            out[0] = clamp8((r.x0 + r.t3) >> 17); out[7] = clamp8((r.x0 - r.t3) >> 17);
-            out[1] = clamp8((r.x1 + r.t2) >> 17); out[6] = clamp8((r.x1 - r.t2) >> 17);
-            out[2] = clamp8((r.x2 + r.t1) >> 17); out[5] = clamp8((r.x2 - r.t1) >> 17);
-            out[3] = clamp8((r.x3 + r.t0) >> 17); out[4] = clamp8((r.x3 - r.t0) >> 17);
+            const W bias(65536 + (128 << 17));
+            r.x0 = r.x0 + bias; r.x1 = r.x1 + bias; r.x2 = r.x2 + bias; r.x3 = r.x3 + bias;
+            out[0] = clamp8((r.x0 + r.t3).shr(17)); out[7] = clamp8((r.x0 - r.t3).shr(17));
+            out[1] = clamp8((r.x1 + r.t2).shr(17)); out[6] = clamp8((r.x1 - r.t2).shr(17));
+            out[2] = clamp8((r.x2 + r.t1).shr(17)); out[5] = clamp8((r.x2 - r.t1).shr(17));
+            out[3] = clamp8((r.x3 + r.t0).shr(17)); out[4] = clamp8((r.x3 - r.t0).shr(17));
         }
     }
 

@@ -165,6 +165,40 @@ def test_reader_rejects_what_it_cannot_decode(jpeg_files):
     assert (w.value, h.value, c.value) == (640, 360, 3) and b"too small" in lib.ssim_imgio_last_error()
 
 
+def test_reader_survives_damaged_files(jpeg_files):
+    """a few hundred mutants (bit flips, stray 0xFF, truncations, damaged headers) of a progressive file and of a baseline
+    4:2:0 one: every call returns -- pixels or ValueError -- and never crashes the process (tools/dev/jpeg_fuzz.cpp is the
+    same loop under AddressSanitizer / UBSan)"""
+    rng = np.random.default_rng(20261017)
+    bases = [jpeg_files["q10"].copy()]
+    try:
+        bases.append(np.frombuffer(_encode(api.decode_jpeg(jpeg_files["q90"])[:96, :160], quality=70, subsampling=2), dtype=np.uint8).copy())
+    except ImportError:
+        pass
+    decoded = 0
+    for base in bases:
+        for _ in range(150):
+            d = base.copy()
+            for _ in range(int(rng.integers(1, 8))):
+                pos = int(rng.integers(0, min(d.size, 700) if rng.integers(0, 4) == 0 else d.size))
+                kind = int(rng.integers(0, 4))
+                if kind == 0:
+                    d[pos] = rng.integers(0, 256)
+                elif kind == 1:
+                    d[pos] ^= 1 << int(rng.integers(0, 8))
+                elif kind == 2:
+                    d[pos] = 0xFF
+                elif d.size > 10:
+                    d = d[:pos + 1].copy()
+            try:
+                img = api.decode_jpeg(d)
+                assert img.ndim in (2, 3) and img.size > 0
+                decoded += 1
+            except ValueError:
+                pass
+    assert decoded > 0
+
+
 def test_cli_reads_jpeg(jpeg_files, decoded, tmp_path):
     from test_cli import fnv
     path = str(tmp_path / "q30.jpg")
