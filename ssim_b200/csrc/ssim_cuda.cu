@@ -462,7 +462,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.a = dA; p.b = dB;
     p.pitchA = (long long)pitchA; p.frameStrideA = (long long)frameStrideA;
     p.pitchB = (long long)pitchB; p.frameStrideB = (long long)frameStrideB;
-    p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride; p.mapStep = (long long)mapStep;
+    p.map = dMap; p.mapPitch = (long long)mapPitch; p.mapFrameStride = (long long)mapFrameStride; p.mapStep = (long long)mapStep; p.mapPitchBytes = (long long)(mapPitch * sizeof(float));
     p.width = (int)width; p.srcRows = (int)srcRows; p.outY0 = (int)outY0; p.outRows = (int)outRows; p.frames = (int)frames;
     p.geo = ssimk::make_slot_geo(plan, width);
     p.frameAcc = ws.frameAcc;
@@ -470,7 +470,7 @@ int compute_device_impl(Context* c, cudaStream_t stream, uint32_t width, uint32_
     p.sums = dSums; p.ssim = dSsim;
     p.invCount = 1.0 / (double)(uint32_t)(width * outRows);    // uint32 product, as src/ssim.cpp:1102
     for (int d = 0; d < 6; ++d) p.g[d] = c->taps[d];
-    p.magic = 0x4B000000u;
+    p.magic = 0x4B000064u;
     {
         static const unsigned backoff = [] { const char* e = getenv("SSIM_CUDA_BACKOFF_NS"); return e ? (unsigned)atoi(e) : ssimk::kBackoffNs; }();
         p.backoffNs = backoff;

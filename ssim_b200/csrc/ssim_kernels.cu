@@ -85,10 +85,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// u8 -> f32 without the conversion pipe: PRMT builds the float 2^23 + byte, the packed FADD that follows removes
-// 2^23 + centre (exact).  I2F.U8 runs at 1/8 rate on B200 (tools/microbench), PRMT is an ALU-pipe op.
-template <int kByte>
-__device__ __forceinline__ float magic_byte(uint32_t word, uint32_t magic) { return __uint_as_float(__byte_perm(word, magic, 0x7440 + kByte)); }
+// u8 -> f32 without the conversion pipe (I2F.U8 runs at 1/8 rate on B200, tools/microbench): PRMT puts pixel bytes under the
+// exponent byte of a float (16-bit pixels: 2^23 + pixel as f32) or of two halves (8-bit pixels: 1024 + pixel as f16x2, one PRMT
+// for two pixels); the add that follows removes the offset together with the centring pixel, exactly.  PRMT costs ~1.4 issue
+// cycles under a packed-FMA stream (profiles/r01_issue_port_microbench.txt), so halving their number is worth 1.5% of the kernel.
+// f16 + f32 -> f32 (mixed-precision add, sm_100: SASS FHADD) on the low / high half of a register
+__device__ __forceinline__ float add_f16lo(uint32_t h2, float c) {
+    float r; asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %1;\nadd.rn.f32.f16 %0, lo, %2;\n}\n" : "=f"(r) : "r"(h2), "f"(c)); return r;
+}
+__device__ __forceinline__ float add_f16hi(uint32_t h2, float c) {
+    float r; asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %1;\nadd.rn.f32.f16 %0, hi, %2;\n}\n" : "=f"(r) : "r"(h2), "f"(c)); return r;
+}
 
 // ------------------------------------------------------------------------------------------------ fused kernel
 // The kernel is PERSISTENT: the grid is one CTA of 8 warp pairs per SM (all resident at once) and every warp pair owns one
@@ -207,7 +214,9 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     // the stage of block `blk` of the current piece is block blk + 2 of the same piece or, in its last two blocks, block 0
     // or 1 of the NEXT piece (every piece has >= 2 blocks), whose geometry and centring pixels are fetched one piece ahead.
     auto issue = [&](const PieceGeo& ge, int blkIdx, uint32_t stage, bool refill, uint32_t emptyParity, bool patched) {
-        if (lane == 0) {
+        uint32_t leader;
+        asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
+        if (leader) {
             // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes).
             // The stage may be refilled once EVERY lane's loads of its previous contents have been performed: each lane
             // releases the stage through an mbarrier (count 32) and lane 0 acquires it before re-arming the TMA barrier.
@@ -267,12 +276,17 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     uint32_t released = 0;                                  // ring halves (global count) handed to the consumer
     #pragma unroll 1
     for (;;) {
-        // (a - ca, b - cb) from the bytes: PRMT builds 2^23 + byte, one packed FADD removes 2^23 + centre (exact)
-        const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));
+        // (a - ca, b - cb) from the bytes, exact: see the widening in the block loop
+        const u64 negMagic = pack2(-(8388608.0f + ca), -(8388608.0f + cb));     // 16-bit pixels
+        const float negCa = -(1024.0f + ca), negCb = -(1024.0f + cb);           // 8-bit pixels
+        uint32_t hpa = 0, hpb = 0;                                              // the current pair of pixels of A / B as f16x2
         const float k2 = -0.5f * p.eps2 * (ca - cb) * (ca - cb);  // see the formula in consumer_warp()
         const bool patchLeft  = (g.bx == 0);
         const bool patchRight = (g.bx + kBandW + kHalo > p.width);
         const bool patched = patchLeft || patchRight;
+        // input row i of the piece lives in ring row ((firstHalf & 1) * 11 + i) mod 22: every piece starts a new half
+        const uint32_t ringLaneEnd = ringBase + hq * 128 + kRingRows * kRingRowBytes;
+        uint32_t ringRowAddr = ringBase + hq * 128 + ((firstHalf & 1u) * kTaps + hr) * kRingRowBytes;
 
         #pragma unroll 1
         for (int blk = 0; blk < g.nBlk; ++blk) {
@@ -336,9 +350,10 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             mbar_arrive(barStageEmpty + 8 * stage);
 
             // ring position of this lane's row (see above)
-            const uint32_t i  = (uint32_t)blk * kBlkRows + hr;
-            const uint32_t ih = i / kTaps, t = i - ih * kTaps;
-            const uint32_t dstRow = ringBase + (((firstHalf + ih) & 1u) * kTaps + t) * kRingRowBytes + hq * 128;
+            // the ring row of this lane's row, kept as an address that advances by 8 rows per block (mod 22 rows)
+            const uint32_t dstRow = ringRowAddr;
+            ringRowAddr += kBlkRows * kRingRowBytes;
+            if (ringRowAddr >= ringLaneEnd) ringRowAddr -= kRingRows * kRingRowBytes;
             uint32_t dst4[4];
             #pragma unroll
             for (int m = 0; m < 4; ++m) dst4[m] = dstRow + ((uint32_t)(m ^ hq) << 3);
@@ -348,21 +363,28 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
             for (int ii = 0; ii < 26; ++ii) {                // input column 16hq - 5 + ii
                 // 8-bit: byte 11 + ii of the 48-byte window; 16-bit: halfword 3 + ii of the 64-byte window
                 const int byteIdx = kU16 ? ii + 3 : ii + 11;
-                float fa, fb;
-                if (kU16) {
-                    // 2^23 + pixel: the two pixel bytes under the two top bytes of the magic word (PRMT with an immediate selector)
+                float a, b;                                             // (a - ca, b - cb), exact
+                if (!kU16) {
+                    // 8-bit: one PRMT makes TWO pixels of an image as f16 values 1024 + byte (bytes {pixel, 0x64, next pixel, 0x64});
+                    // the mixed-precision add f16 + f32 -> f32 (SASS FHADD) takes 1024 + centre off again on the way to f32.
+                    // Pairs start at even bytes (ii odd); the first and the last column of the window are singles.
+                    if (ii == 0 || (ii & 1)) {
+                        if ((byteIdx & 3) == 3)  { hpa = __byte_perm(wa[byteIdx >> 2], magic, 0x4343); hpb = __byte_perm(wb[byteIdx >> 2], magic, 0x4343); }
+                        else if (byteIdx & 2)    { hpa = __byte_perm(wa[byteIdx >> 2], magic, 0x4342); hpb = __byte_perm(wb[byteIdx >> 2], magic, 0x4342); }
+                        else                     { hpa = __byte_perm(wa[byteIdx >> 2], magic, 0x4140); hpb = __byte_perm(wb[byteIdx >> 2], magic, 0x4140); }
+                        a = add_f16lo(hpa, negCa); b = add_f16lo(hpb, negCb);
+                    } else {
+                        a = add_f16hi(hpa, negCa); b = add_f16hi(hpb, negCb);
+                    }
+                } else {
+                    // 16-bit: 2^23 + pixel as f32 -- the two pixel bytes under the two top bytes of the magic word (PRMT with an
+                    // immediate selector) -- and one packed FADD that removes 2^23 + centre
+                    float fa, fb;
                     if (byteIdx & 1) { fa = __uint_as_float(__byte_perm(wa[byteIdx >> 1], magic, 0x7632)); fb = __uint_as_float(__byte_perm(wb[byteIdx >> 1], magic, 0x7632)); }
                     else             { fa = __uint_as_float(__byte_perm(wa[byteIdx >> 1], magic, 0x7610)); fb = __uint_as_float(__byte_perm(wb[byteIdx >> 1], magic, 0x7610)); }
-                } else {
-                    switch (byteIdx & 3) {
-                        case 0:  fa = magic_byte<0>(wa[byteIdx >> 2], magic); fb = magic_byte<0>(wb[byteIdx >> 2], magic); break;
-                        case 1:  fa = magic_byte<1>(wa[byteIdx >> 2], magic); fb = magic_byte<1>(wb[byteIdx >> 2], magic); break;
-                        case 2:  fa = magic_byte<2>(wa[byteIdx >> 2], magic); fb = magic_byte<2>(wb[byteIdx >> 2], magic); break;
-                        default: fa = magic_byte<3>(wa[byteIdx >> 2], magic); fb = magic_byte<3>(wb[byteIdx >> 2], magic); break;
-                    }
+                    unpack2(add2(pack2(fa, fb), negMagic), a, b);
                 }
-                const u64 ab = add2(pack2(fa, fb), negMagic);          // (a - ca, b - cb), exact
-                float a, b; unpack2(ab, a, b);
+                const u64 ab = pack2(a, b);
                 const float d = a - b;
                 const u64 sp = pack2(fmaf(d, d, k2), a * b);           // ((a'-b')^2 + k2, a'b')
                 #pragma unroll

@@ -27,8 +27,11 @@ constexpr int kStages      = 2;    // TMA stages per warp pair
 // worse on 16 x 4K, and was dropped.)
 constexpr int kPairsPerCta = 8;    // warp pairs per CTA: each is one producer warp and one consumer warp
 constexpr int kCtaThreads  = 2 * kPairsPerCta * 32;      // 512: warps 0-7 producers (TMA + horizontal pass), 8-15 consumers
-constexpr int kProducerRegs = 96;  // setmaxnreg budgets of the two warpgroups: 128*96 + 128*160 = 256*128
-constexpr int kConsumerRegs = 160;
+// setmaxnreg budgets of the two warpgroups: 128*120 + 128*136 = 256*128.  Measured on 64 x 4K pairs (profiles/r02_variants.txt):
+// 96/160 2062 us, 112/144 2056, 120/136 2038, 128/128 2074 -- the producer stops re-deriving per-lane constants in every block,
+// the consumer's 88 accumulators + formula temporaries still fit without spills.
+constexpr int kProducerRegs = 120;
+constexpr int kConsumerRegs = 136;
 constexpr unsigned kBackoffNs = 200; // default sleep between polls of the partner warp's mbarrier
 constexpr int kRingPlaneBytes = kBandW * 8;              // 512: one row of packed {x, y} pairs
 constexpr int kRingRowPad     = 32;                      // consecutive rows start 8 banks apart: see the ring layout in the kernel
@@ -234,6 +237,9 @@ struct FusedParams {
     float*  map;             // NULL when no map is wanted
     long long mapPitch, mapFrameStride;   // floats
     long long mapStep;       // floats between horizontally adjacent map values (1 = dense rows)
+    long long mapPitchBytes; // mapPitch in bytes.  The kernel shifts mapPitch itself and does not read this field, but it stays: where
+                             // the fields behind it sit changes ptxas' register allocation in the consumer body (1125 instead of
+                             // 1110 instructions per 11 rows without it; 64 x 4K 2043 instead of 2036 us, profiles/r02_variants.txt)
     int width, srcRows, outY0, outRows, frames;
     SlotGeo geo;
     // reduction workspace (per stream): one word per frame, zero before the launch and again after it: slot count in the
@@ -243,7 +249,9 @@ struct FusedParams {
     double*   sums;          // out, may be NULL: [frames] sum of the SSIM values of each frame
     float*    ssim;          // out, may be NULL: [frames] float(sum * invCount)
     double    invCount;      // 1 / double(uint32(width*outRows))
-    float g[6];              // separable 11-tap weights: g[d] is the tap at distance d from the centre
+    alignas(16) float g[6];  // separable 11-tap weights: g[d] is the tap at distance d from the centre.  16-byte aligned: the hot loops
+                             // re-load the taps from the constant bank (one LDCU.128 + one LDCU.64; three loads when the array
+                             // sits at an odd multiple of 8 bytes: 2063 instead of 2036 us on 64 x 4K, profiles/r02_variants.txt)
     uint32_t magic;          // 0x4B000000 (float 2^23): kept opaque to ptxas, see the kernel
     uint32_t backoffNs;      // sleep between polls of the partner warp's mbarrier
     float eps2;              // 2*((sum of the 11x11 window) - 1): the reference window's normalisation bias, ~2.05e-8
