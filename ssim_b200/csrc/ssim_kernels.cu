@@ -3,7 +3,7 @@
 // ssim_fused_kernel replaces, in ONE launch, the reference's per-tile pipeline
 //   retrieve_tile (src/ssim.cpp:515-583)  ->  TMA box loads of u8 rows (+5 px halo) into shared memory,
 //                                             clamp-to-edge by coordinate clamping (rows) / patching (columns),
-//                                             u8 -> f32 widening with PRMT + one packed FADD (centred on a per-item pixel)
+//                                             u8 -> f32 widening with PRMT + a mixed-precision add (centred on a per-item pixel)
 //   multiply x3   (src/ssim.cpp:249-265)  ->  a'^2 + b'^2 and a'b' in registers (never materialised)
 //   gaussian_blur x5 (src/ssim.cpp:321-489, src/ssim_fma.cpp:106-273)
 //                                         ->  separable 11-tap horizontal pass (registers -> swizzled smem ring)
@@ -114,7 +114,7 @@ __device__ __forceinline__ float add_f16hi(uint32_t h2, float c) {
 //                               the frame writes the result and (strips across GPUs) exchanges it with the peers over NVLink
 //
 // The two roles overlap in time (the consumer's dependent formula chain hides behind the producer's FMAs and vice versa),
-// setmaxnreg moves registers from the producers (96) to the consumers (160), and nothing is ever synchronised CTA-wide
+// setmaxnreg moves registers from the producers (120) to the consumers (136), and nothing is ever synchronised CTA-wide
 // after the prologue.  Every hand-over (TMA stage full/empty, ring half full/empty) is an mbarrier on which each lane
 // releases its own accesses and each lane acquires for itself: see the protocol table in DESIGN.md section 4.
 //
@@ -214,12 +214,14 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
     // the stage of block `blk` of the current piece is block blk + 2 of the same piece or, in its last two blocks, block 0
     // or 1 of the NEXT piece (every piece has >= 2 blocks), whose geometry and centring pixels are fetched one piece ahead.
     auto issue = [&](const PieceGeo& ge, int blkIdx, uint32_t stage, bool refill, uint32_t emptyParity, bool patched) {
+        // one elected lane of the (converged) warp: with elect.sync ptxas emits the issue sequence once, behind one branch;
+        // `lane == 0` made it wrap every UTMALDG in a loop that broadcasts the five operands lane by lane (-0.5% kernel time)
         uint32_t leader;
         asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(leader));
         if (leader) {
             // TMA goes through the uniform datapath: one lane, warp-uniform operands (never issue it from divergent lanes).
             // The stage may be refilled once EVERY lane's loads of its previous contents have been performed: each lane
-            // releases the stage through an mbarrier (count 32) and lane 0 acquires it before re-arming the TMA barrier.
+            // releases the stage through an mbarrier (count 32) and the elected lane acquires it before re-arming the TMA barrier.
             // Program order plus __syncwarp() is not enough here -- with the refill issued straight after the loads,
             // tools/dev/stress.py saw rare 8-row x 16-column blocks computed from the NEXT box's bytes.
             if (refill) {
@@ -346,7 +348,7 @@ __device__ __forceinline__ void producer_warp(const CUtensorMap* tmA, const CUte
                 wb[4 * q] = vb.x; wb[4 * q + 1] = vb.y; wb[4 * q + 2] = vb.z; wb[4 * q + 3] = vb.w;
             }
             // every lane releases the stage (the acquire + refill sit at ii == 10 below: by then the 32 arrivals have long
-            // drained and lane 0 never spins)
+            // drained and the issuing lane never spins)
             mbar_arrive(barStageEmpty + 8 * stage);
 
             // ring position of this lane's row (see above)
