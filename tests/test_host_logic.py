@@ -189,3 +189,46 @@ def test_hot_code_of_the_fused_kernel_fits_the_instruction_cache():
     assert len(sizes) == 5, r.stdout                      # five instantiations of ssim_fused_kernel
     assert max(sizes) < 32.0, sizes
     assert r.stdout.count("no local-memory spills") >= 5, r.stdout       # and none of them spills
+
+
+def _byte_perm(x, y, sel):
+    """CUDA's __byte_perm / PTX prmt.b32 (default mode): result byte k = byte (nibble k of sel) of the 8-byte pool {y, x}."""
+    pool = [(x >> (8 * i)) & 0xff for i in range(4)] + [(y >> (8 * i)) & 0xff for i in range(4)]
+    return sum(pool[(sel >> (4 * k)) & 7] << (8 * k) for k in range(4))
+
+
+def test_pixel_widening_tricks_are_exact():
+    """The producer's pixel -> f32 conversions (ssim_kernels.cu, "Widening") restated on the CPU.  8-bit: one PRMT with the magic
+    word 0x4B000064 puts two pixels under the f16 exponent byte 0x64 (= 1024 + pixel each), the mixed-precision add
+    f16 + f32 -> f32 with -(1024 + centre) leaves pixel - centre; the 26 columns a lane needs are bytes 11..36 of its 48-byte
+    window, taken as one single, twelve pairs, one single.  16-bit: selectors 0x7610 / 0x7632 put a pixel under 0x4B00 (2^23 + pixel
+    as f32).  Everything must be exact for every pixel / centre value."""
+    import numpy as np
+    magic = 0x4B000064
+    # f16 bit pattern 0x64pp is 1024 + pp, and the add is exact in f32 for every pixel and centre
+    p = np.arange(256, dtype=np.uint16)
+    h = (np.uint16(0x6400) | p).view(np.float16)
+    assert np.array_equal(h.astype(np.float32), 1024.0 + p.astype(np.float32))
+    for c in range(256):
+        neg = np.float32(-(1024.0 + c))
+        assert np.array_equal(h.astype(np.float32) + neg, p.astype(np.float32) - np.float32(c))
+    # the pairing schedule of the kernel's column loop over a window of 48 bytes held in 12 words
+    rng = np.random.default_rng(5)
+    window = rng.integers(0, 256, 48, dtype=np.uint8)
+    words = [int.from_bytes(window[4 * i:4 * i + 4].tobytes(), "little") for i in range(12)]
+    got, hp = [], 0
+    for ii in range(26):
+        byte_idx = ii + 11
+        if ii == 0 or (ii & 1):
+            sel = 0x4343 if (byte_idx & 3) == 3 else 0x4342 if (byte_idx & 2) else 0x4140
+            hp = _byte_perm(words[byte_idx >> 2], magic, sel)
+            half = hp & 0xffff
+        else:
+            half = hp >> 16
+        assert half >> 8 == 0x64
+        got.append(half & 0xff)
+    assert got == [int(v) for v in window[11:37]]
+    # 16-bit pixels: 2^23 + pixel as f32 bits
+    w = 0xBEEF1234
+    lo, hi = _byte_perm(w, magic, 0x7610), _byte_perm(w, magic, 0x7632)
+    assert np.array([lo, hi], dtype=np.uint32).view(np.float32).tolist() == [8388608.0 + 0x1234, 8388608.0 + 0xBEEF]
